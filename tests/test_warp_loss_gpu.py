@@ -176,11 +176,12 @@ def test_full_size_kitti_batch_vs_oracle():
     p, q = lf.compute_photo_and_geometry_loss(tgt, refs, K, td, rd, ps, pi, 1, 1, 1, 1, "zeros")
     s = lf.compute_smooth_loss(td, tgt, rd, refs)
     np.testing.assert_allclose([float(p), float(q), float(s)], [float(p0), float(q0), float(s0)], rtol=1e-4)
-    # property: zero motion and identical constant depth => depth inconsistency is exactly 0 everywhere
+    # property: zero motion and identical constant depth => depth inconsistency vanishes (border mode:
+    # with 'zeros' the half-out-of-image taps of the (W-1)-normalised edge pixels sample 0, as in the reference)
     const = [torch.full_like(td[0], 0.7)]
     zero = [torch.zeros_like(ps[0])] * 2
-    _, q_id = lf.compute_photo_and_geometry_loss(tgt, refs, K, const, [const, const], zero, zero, 1, 1, 1, 0, "zeros")
-    assert abs(float(q_id)) < 1e-6
+    _, q_id = lf.compute_photo_and_geometry_loss(tgt, refs, K, const, [const, const], zero, zero, 1, 1, 1, 0, "border")
+    assert abs(float(q_id)) < 1e-5
     # property: the sum over pair-directions is the sum of single-direction calls
     parts = [lf.compute_pairwise_loss(tgt, refs[i], td[0], rd[i][0], ps[i], K, 1, 1, 1, "zeros") for i in range(2)]
     parts += [lf.compute_pairwise_loss(refs[i], tgt, rd[i][0], td[0], pi[i], K, 1, 1, 1, "zeros") for i in range(2)]
