@@ -125,6 +125,90 @@ int scsfm_smooth_fwd(const ScsfmSmoothJob* jobs_host, int njobs, int B, int H, i
 int scsfm_smooth_bwd(const ScsfmSmoothJob* jobs_host, int njobs, int B, int H, int W, void* stats,
                      const float* grad_out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Network operators (DispResNet / PoseResNet forward + backward).  Activations are NHWC fp32,
+ * conv weights [Cout][kh][kw][Cin] (the reference's OIHW parameters stored channels-last).
+ * These replace the cuDNN / ATen kernels PyTorch launches for reference models/resnet_encoder.py:87-97,
+ * models/DispResNet.py:13-47,85-101 and models/PoseResNet.py:35-51 (rows K1-K5 of SURVEY.md 2.3).
+ * ---------------------------------------------------------------------------------------------- */
+#define SCSFM_PADMODE_ZERO 0
+#define SCSFM_PADMODE_REFLECT 1   /* nn.ReflectionPad2d(1), DispResNet.py:34 */
+#define SCSFM_ACT_NONE 0
+#define SCSFM_ACT_RELU 1
+#define SCSFM_ACT_ELU 2           /* nn.ELU, DispResNet.py:20 */
+#define SCSFM_ACT_DISP 3          /* 10*sigmoid(x)+0.01, DispResNet.py:98 */
+
+typedef struct ScsfmConv {
+    /* forward operands */
+    const float* in;      /* [B,Hi,Wi,Cin] */
+    const float* w;       /* [Cout,kh,kw,Cin] */
+    const float* bias;    /* [Cout] or NULL */
+    float* out;           /* [B,Ho,Wo,Cout] */
+    /* backward operands */
+    const float* dout;    /* [B,Ho,Wo,Cout] gradient of the PRE-activation output */
+    float* din;           /* dgrad result [B,Hi,Wi,Cin] (overwritten) */
+    const float* addend;  /* optional tensor added to din (residual branch gradient) */
+    float* dw;            /* [Cout,kh,kw,Cin], accumulated into (atomic +=) */
+    float* dbias;         /* [Cout] or NULL, accumulated into */
+    /* fused BatchNorm statistics of the forward output: sums[g][c] = {sum, sum of squares}, fp64,
+     * accumulated into (caller zeroes).  Samples are split into bn_groups equal groups (one per
+     * network call when several calls are batched into one launch). */
+    double* bn_sums;
+    int bn_groups;
+    int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, pad_mode, act;
+} ScsfmConv;
+
+/* Exact-fp32 implicit-GEMM convolution on CUDA cores (every shape). */
+int scsfm_conv2d_fwd_simt(const ScsfmConv* p, void* stream);
+int scsfm_conv2d_dgrad_simt(const ScsfmConv* p, void* stream);
+int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
+
+/* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
+int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);
+/* NHWC [B,H,W,C] -> NCHW */
+int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, void* stream);
+
+/* BatchNorm2d (torchvision resnet.py blocks): prepare per-channel scale/shift from the fused batch sums
+ * (training; updates running stats with `momentum`, unbiased variance) or from the running stats (eval).
+ * saved[g][c] = {scale, shift, mean, invstd}. */
+int scsfm_bn_prepare(const double* sums, int groups, int C, long long count_per_group, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                     int training, float* saved, void* stream);
+/* z = relu?(y*scale + shift + residual) */
+int scsfm_bn_apply(const float* y, const float* saved, const float* residual, float* z, long long rows, int C,
+                   int groups, int relu, void* stream);
+/* backward: given dz (gradient of z), z, y -> dy (overwrites `dy`), dres (= dz masked by relu; may be NULL or
+ * alias dz), dgamma/dbeta accumulated into. `work` holds groups*C*2 doubles. */
+int scsfm_bn_backward(const float* dz, const float* z, const float* y, const float* saved, const float* gamma,
+                      float* dy, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
+                      int relu, double* work, void* stream);
+
+/* MaxPool2d(3, 2, 1) (resnet_encoder.py:93): idx stores the argmax tap (0..8) per output element. */
+int scsfm_maxpool_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* idx, void* stream);
+int scsfm_maxpool_bwd(const float* dy, const unsigned char* idx, int B, int H, int W, int C, float* dx, int accumulate,
+                      void* stream);
+
+/* nearest x2 upsample of `lo` concatenated with `skip` on channels (DispResNet.py:92-95). skip may be NULL. */
+int scsfm_upcat_fwd(const float* lo, const float* skip, int B, int H, int W, int C1, int C2, float* out, void* stream);
+/* Backward of ReflectionPad2d(1) (+ optional upsample/concat): dpad is the gradient w.r.t. the padded tensor
+ * [B,H+2,W+2,C1+C2].  d_lo [B,H/2,W/2,C1] (overwritten; multiplied by act'(lo_act) if act != NONE),
+ * d_skip [B,H,W,C2] overwritten.  With C2 == 0 and upsample == 0: plain fold into d_lo [B,H,W,C1]
+ * (accumulate flag honoured, act applied after accumulation). */
+int scsfm_fold_bwd(const float* dpad, int B, int H, int W, int C1, int C2, int upsample, float* d_lo,
+                   const float* lo_act, int act, int accumulate, float* d_skip, void* stream);
+
+/* in place: d *= act'(out) where `out` is the activation OUTPUT (relu / elu / disp-sigmoid). */
+int scsfm_act_bwd(float* d, const float* out, long long n, int act, void* stream);
+
+/* pose head (PoseResNet.py:47-49): out[b,c] = scale * mean_hw x[b,hw,c]; backward broadcasts. */
+int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, float scale, float* out, void* stream);
+int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream);
+
+/* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena. step >= 1. */
+int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

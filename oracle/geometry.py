@@ -82,6 +82,12 @@ def project(cam, rot, tr, padding_mode):
     return xn.view(B, H, W), yn.view(B, H, W), Z.view(B, 1, H, W)
 
 
+# When True, bilinear_sample / the SSIM box filter call the library kernels the reference itself calls
+# (F.grid_sample, F.avg_pool2d) instead of the tap-by-tap restatement.  tests/test_oracle_golden.py checks the
+# two agree; bench.py's CPU baseline uses the fast form so that the timed CPU path is the reference's own.
+USE_LIBRARY_KERNELS = False
+
+
 def bilinear_sample(src, xn, yn, padding_mode):
     """torch.nn.functional.grid_sample(src, (xn,yn), 'bilinear', padding_mode, align_corners=False)
     written out tap by tap (call sites: reference inverse_warp.py:262,267).
@@ -92,6 +98,9 @@ def bilinear_sample(src, xn, yn, padding_mode):
     (1-fx)(1-fy) ...; any neighbour outside the image contributes value 0 (and no
     gradient).  src [B,C,H,W]; xn, yn [B,Ho,Wo] -> [B,C,Ho,Wo].
     """
+    if USE_LIBRARY_KERNELS:
+        return torch.nn.functional.grid_sample(src, torch.stack([xn, yn], -1), mode="bilinear", padding_mode=padding_mode,
+                                               align_corners=False)
     B, C, H, W = src.shape
     ix = ((xn + 1) * W - 1) / 2
     iy = ((yn + 1) * H - 1) / 2

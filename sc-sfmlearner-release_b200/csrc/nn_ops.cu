@@ -1,0 +1,548 @@
+// HBM-bound network operators around the convolutions: layout change, BatchNorm apply / backward,
+// max-pool, nearest-upsample + concat, reflection-pad gradient fold, activation gradients, the pose
+// head's spatial mean and Adam.  All NHWC fp32, float4 accesses where the channel count allows.
+//
+// Replaces ATen/cuDNN kernels reached from reference resnet_encoder.py:87-97 (bn, relu, maxpool),
+// DispResNet.py:34,47,95 (ReflectionPad2d, interpolate, cat), PoseResNet.py:47-49 and
+// train.py:176-178,280-282 (Adam) -- rows K2-K5, K11 of SURVEY.md section 2.3.
+#include "nn_common.cuh"
+
+namespace scsfm {
+
+constexpr int NT = 256;
+
+static inline int grid_for(long long n, int per_cta = NT) {
+    long long g = (n + per_cta - 1) / per_cta;
+    if (g > 148LL * 32) g = 148 * 32;   // grid-stride beyond 32 CTAs per SM
+    return (int)(g < 1 ? 1 : g);
+}
+
+// ----- layout ---------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int C, int HW,
+                                    float* __restrict__ out) {
+    const int nsrc = b ? 2 : 1, Ct = C * nsrc;
+    const long long total = (long long)B * HW * Ct;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % Ct);
+        const long long px = i / Ct;
+        const int bb = (int)(px / HW), p = (int)(px - (long long)bb * HW);
+        const float* src = c < C ? a : b;
+        const int cc = c < C ? c : c - C;
+        out[i] = __ldg(src + ((size_t)bb * C + cc) * HW + p);
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int C, int HW, float* __restrict__ out) {
+    const long long total = (long long)B * HW * C;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int p = (int)(i % HW);
+        const long long bc = i / HW;
+        const int c = (int)(bc % C), bb = (int)(bc / C);
+        out[i] = __ldg(in + ((size_t)bb * HW + p) * C + c);
+    }
+}
+
+// ----- BatchNorm --------------------------------------------------------------------------------
+// saved[g][c] = {scale, shift, mean, invstd}
+__global__ void bn_prepare_kernel(const double* __restrict__ sums, int G, int C, double count, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                  float momentum, float eps, int training, float* __restrict__ saved) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float g = gamma[c], bt = beta[c];
+    if (training) {
+        float rm = rmean[c], rv = rvar[c];
+        for (int grp = 0; grp < G; ++grp) {
+            const double s = sums[((size_t)grp * C + c) * 2], q = sums[((size_t)grp * C + c) * 2 + 1];
+            const double mean = s / count;
+            double var = q / count - mean * mean;
+            if (var < 0) var = 0;
+            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+            float* o = saved + ((size_t)grp * C + c) * 4;
+            o[0] = g * invstd;
+            o[1] = bt - (float)mean * g * invstd;
+            o[2] = (float)mean;
+            o[3] = invstd;
+            // running statistics: one update per network call, in call order (nn.BatchNorm2d, momentum 0.1)
+            const double unbiased = count > 1 ? var * count / (count - 1) : var;
+            rm = (1.f - momentum) * rm + momentum * (float)mean;
+            rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+        }
+        rmean[c] = rm;
+        rvar[c] = rv;
+    } else {
+        const float invstd = 1.0f / sqrtf(rvar[c] + eps);
+        for (int grp = 0; grp < G; ++grp) {
+            float* o = saved + ((size_t)grp * C + c) * 4;
+            o[0] = g * invstd;
+            o[1] = bt - rmean[c] * g * invstd;
+            o[2] = rmean[c];
+            o[3] = invstd;
+        }
+    }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ saved, const float* __restrict__ res,
+                                float* __restrict__ z, long long rows, int C, long long rows_per_group, int relu) {
+    const int C4 = C >> 2;
+    const long long total = rows * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const long long r = i / C4;
+        const int c = (int)(i - r * C4) * 4;
+        const int g = (int)(r / rows_per_group);
+        const float* sv = saved + ((size_t)g * C + c) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
+        float o[4] = {v.x * sv[0] + sv[1], v.y * sv[4] + sv[5], v.z * sv[8] + sv[9], v.w * sv[12] + sv[13]};
+        if (res) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + i);
+            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        reinterpret_cast<float4*>(z)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// pass 1: work[g][c] = { sum dz', sum dz' * xhat }  (dz' = dz gated by relu)
+__global__ void __launch_bounds__(NT)
+bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
+                     const float* __restrict__ saved, long long rows_per_group, int C, int relu, int rows_per_cta,
+                     double* __restrict__ work) {
+    // blockIdx.y = group, blockIdx.z = 64-channel slab, blockIdx.x = row chunk
+    const int g = blockIdx.y, c = blockIdx.z * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
+    const long long r0 = (long long)g * rows_per_group + (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min((long long)(g + 1) * rows_per_group, r0 + rows_per_cta);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C) {
+        const float mean = saved[((size_t)g * C + c) * 4 + 2], invstd = saved[((size_t)g * C + c) * 4 + 3];
+        for (long long r = r0 + rl; r < r1; r += NT / 64) {
+            float d = __ldg(dz + r * C + c);
+            if (relu && !(__ldg(z + r * C + c) > 0.f)) d = 0.f;
+            s0 += d;
+            s1 += d * ((__ldg(y + r * C + c) - mean) * invstd);
+        }
+    }
+    __shared__ float sh[2][NT];
+    sh[0][threadIdx.x] = s0;
+    sh[1][threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < C) {
+        const float a = sh[0][threadIdx.x] + sh[0][threadIdx.x + 64] + sh[0][threadIdx.x + 128] + sh[0][threadIdx.x + 192];
+        const float b = sh[1][threadIdx.x] + sh[1][threadIdx.x + 64] + sh[1][threadIdx.x + 128] + sh[1][threadIdx.x + 192];
+        atomicAdd(work + ((size_t)g * C + c) * 2, (double)a);
+        atomicAdd(work + ((size_t)g * C + c) * 2 + 1, (double)b);
+    }
+}
+
+// pass 2: dy = gamma*invstd*(dz' - mean(dz') - xhat*mean(dz' xhat)); dres = dz'
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
+                                    const float* __restrict__ saved, const double* __restrict__ work, float* __restrict__ dy,
+                                    float* __restrict__ dres, long long rows, int C, long long rows_per_group, int relu) {
+    const int C4 = C >> 2;
+    const long long total = rows * C4;
+    const float inv_n = 1.0f / (float)rows_per_group;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const long long r = i / C4;
+        const int c = (int)(i - r * C4) * 4;
+        const int g = (int)(r / rows_per_group);
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dz) + i);
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(y) + i);
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+        if (relu) {
+            const float4 z4 = __ldg(reinterpret_cast<const float4*>(z) + i);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (!(zz[j] > 0.f)) d[j] = 0.f;
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* sv = saved + ((size_t)g * C + c + j) * 4;
+            const double* w = work + ((size_t)g * C + c + j) * 2;
+            const float xhat = (yy[j] - sv[2]) * sv[3];
+            o[j] = sv[0] * (d[j] - (float)w[0] * inv_n - xhat * (float)w[1] * inv_n);
+        }
+        if (dres) reinterpret_cast<float4*>(dres)[i] = make_float4(d[0], d[1], d[2], d[3]);
+        reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ work, int G, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0, b = 0;
+    for (int g = 0; g < G; ++g) {
+        a += work[((size_t)g * C + c) * 2];
+        b += work[((size_t)g * C + c) * 2 + 1];
+    }
+    if (dbeta) dbeta[c] += (float)a;
+    if (dgamma) dgamma[c] += (float)b;
+}
+
+// ----- max-pool 3x3 stride 2 pad 1 --------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                                   float* __restrict__ y, unsigned char* __restrict__ idx) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        unsigned char bi[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int h = ho * 2 + dy - 1;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int w = wo * 2 + dx - 1;
+                if (w < 0 || w >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C + c));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (vv[j] > best[j] || vv[j] != vv[j]) { best[j] = vv[j]; bi[j] = (unsigned char)(dy * 3 + dx); }
+            }
+        }
+        reinterpret_cast<float4*>(y)[i] = make_float4(best[0], best[1], best[2], best[3]);
+        reinterpret_cast<uchar4*>(idx)[i] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+    }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, int B, int H, int W,
+                                   int C, int Ho, int Wo, float* __restrict__ dx, int accumulate) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // output windows that contain (h, w): ho in {(h+1)/2 - 1 .. (h+1)/2}, tap dy = h + 1 - 2*ho
+        for (int ho = (h + 1) / 2 - 1; ho <= (h + 1) / 2; ++ho) {
+            const int dyy = h + 1 - 2 * ho;
+            if (ho < 0 || ho >= Ho || dyy < 0 || dyy > 2) continue;
+            for (int wo = (w + 1) / 2 - 1; wo <= (w + 1) / 2; ++wo) {
+                const int dxx = w + 1 - 2 * wo;
+                if (wo < 0 || wo >= Wo || dxx < 0 || dxx > 2) continue;
+                const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
+                const uchar4 k = *reinterpret_cast<const uchar4*>(idx + o);
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o));
+                const unsigned char me = (unsigned char)(dyy * 3 + dxx);
+                if (k.x == me) acc[0] += g.x;
+                if (k.y == me) acc[1] += g.y;
+                if (k.z == me) acc[2] += g.z;
+                if (k.w == me) acc[3] += g.w;
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(dx) + i;
+        if (accumulate) {
+            const float4 old = *dst;
+            acc[0] += old.x; acc[1] += old.y; acc[2] += old.z; acc[3] += old.w;
+        }
+        *dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+// ----- nearest x2 upsample + channel concat -----------------------------------------------------
+__global__ void upcat_fwd_kernel(const float* __restrict__ lo, const float* __restrict__ skip, int B, int H, int W, int C1,
+                                 int C2, float* __restrict__ out) {
+    const int Ct4 = (C1 + C2) >> 2, C14 = C1 >> 2;
+    const long long total = (long long)B * H * W * Ct4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c4 = (int)(i % Ct4);
+        long long t = i / Ct4;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float4 v;
+        if (c4 < C14) v = __ldg(reinterpret_cast<const float4*>(lo + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * C1) + c4);
+        else v = __ldg(reinterpret_cast<const float4*>(skip + (((size_t)b * H + h) * W + w) * C2) + (c4 - C14));
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+__device__ __forceinline__ float act_grad(float out, int act) {
+    switch (act) {
+        case ACT_RELU: return out > 0.f ? 1.f : 0.f;
+        case ACT_ELU: return out > 0.f ? 1.f : out + 1.f;          // d/dx elu = exp(x) = elu(x)+1 for x<=0
+        case ACT_DISP: { const float s = (out - 0.01f) * 0.1f; return 10.f * s * (1.f - s); }
+        default: return 1.f;
+    }
+}
+
+// gradient of the reflect-padded tensor folded back onto pixel (h, w): the pixel itself plus the mirrored
+// border entries (pad row -1 mirrors row 1, pad row H mirrors row H-2; same for columns)
+__device__ __forceinline__ float4 fold_at(const float* __restrict__ dpad, int b, int h, int w, int H, int W, int Ct, int c) {
+    const int Hp = H + 2, Wp = W + 2;
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = h + 1;
+    if (h == 1) ys[ny++] = 0;
+    if (h == H - 2) ys[ny++] = H + 1;
+    xs[nx++] = w + 1;
+    if (w == 1) xs[nx++] = 0;
+    if (w == W - 2) xs[nx++] = W + 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dpad + (((size_t)b * Hp + ys[iy]) * Wp + xs[ix]) * Ct + c));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    return a;
+}
+
+// plain fold: d[b,h,w,c] (+)= fold(dpad); then *= act'(act_out)
+__global__ void fold_plain_kernel(const float* __restrict__ dpad, int B, int H, int W, int C, float* __restrict__ d,
+                                  const float* __restrict__ act_out, int act, int accumulate) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float4 a = fold_at(dpad, b, h, w, H, W, C, c);
+        float4* dst = reinterpret_cast<float4*>(d) + i;
+        if (accumulate) { const float4 o = *dst; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+        if (act != ACT_NONE) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(act_out) + i);
+            a.x *= act_grad(q.x, act); a.y *= act_grad(q.y, act); a.z *= act_grad(q.z, act); a.w *= act_grad(q.w, act);
+        }
+        *dst = a;
+    }
+}
+
+// upsample+concat fold, low-resolution part: d_lo[b,h2,w2,c] = sum_{2x2} fold(dpad)[.., c] * act'(lo_act)
+__global__ void fold_up_lo_kernel(const float* __restrict__ dpad, int B, int H, int W, int C1, int Ct, float* __restrict__ d_lo,
+                                  const float* __restrict__ lo_act, int act) {
+    const int C4 = C1 >> 2, H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)B * H2 * W2 * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int w2 = (int)(t % W2); t /= W2;
+        const int h2 = (int)(t % H2);
+        const int b = (int)(t / H2);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const float4 v = fold_at(dpad, b, 2 * h2 + dy, 2 * w2 + dx, H, W, Ct, c);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+        if (act != ACT_NONE) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(lo_act) + i);
+            a.x *= act_grad(q.x, act); a.y *= act_grad(q.y, act); a.z *= act_grad(q.z, act); a.w *= act_grad(q.w, act);
+        }
+        reinterpret_cast<float4*>(d_lo)[i] = a;
+    }
+}
+
+// upsample+concat fold, skip part: d_skip[b,h,w,c] = fold(dpad)[.., C1 + c]   (each skip feeds one conv)
+__global__ void fold_up_skip_kernel(const float* __restrict__ dpad, int B, int H, int W, int C1, int C2, float* __restrict__ d_skip) {
+    const int C4 = C2 >> 2;
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        const float4 a = fold_at(dpad, b, h, w, H, W, C1 + C2, C1 + c);
+        reinterpret_cast<float4*>(d_skip)[i] = a;
+    }
+}
+
+__global__ void act_bwd_kernel(float* __restrict__ d, const float* __restrict__ out, long long n, int act) {
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT)
+        d[i] *= act_grad(__ldg(out + i), act);
+}
+
+// ----- pose head --------------------------------------------------------------------------------
+__global__ void spatial_mean_fwd_kernel(const float* __restrict__ x, int HW, int C, float scale, float* __restrict__ out) {
+    // one CTA per (b, c)
+    __shared__ float red[32];
+    const int b = blockIdx.x / C, c = blockIdx.x % C;
+    float acc = 0.f;
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) acc += __ldg(x + ((size_t)b * HW + p) * C + c);
+    acc = block_sum<NT / 32>(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = scale * (acc / (float)HW);
+}
+
+__global__ void spatial_mean_bwd_kernel(const float* __restrict__ dout, int B, int HW, int C, float scale, float* __restrict__ dx) {
+    const long long total = (long long)B * HW * C;
+    const float k = scale / (float)HW;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        const int b = (int)(i / ((long long)HW * C));
+        dx[i] = __ldg(dout + b * C + c) * k;
+    }
+}
+
+// ----- Adam ---------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    // torch.optim.Adam (non-amsgrad): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+    // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+    const float step_size = lr / bc1;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        float gr = g[i];
+        const float pp = p[i];
+        if (wd != 0.f) gr += wd * pp;
+        const float mm = b1 * m[i] + (1.f - b1) * gr;
+        const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+        m[i] = mm;
+        v[i] = vv;
+        p[i] = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    }
+}
+
+}  // namespace scsfm
+
+using namespace scsfm;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream) {
+    SCSFM_CHECK_ARG(a && out && B > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+    const long long n = (long long)B * H * W * C * (b ? 2 : 1);
+    nchw_to_nhwc_kernel<<<grid_for(n), NT, 0, ST>>>(a, b, B, C, H * W, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, void* stream) {
+    SCSFM_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad arguments");
+    nhwc_to_nchw_kernel<<<grid_for((long long)B * H * W * C), NT, 0, ST>>>(in, B, C, H * W, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_bn_prepare(const double* sums, int groups, int C, long long count_per_group, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                int training, float* saved, void* stream) {
+    SCSFM_CHECK_ARG(gamma && beta && running_mean && running_var && saved && groups > 0 && C > 0, "bn_prepare: bad arguments");
+    SCSFM_CHECK_ARG(!training || (sums && count_per_group > 0), "bn_prepare: training mode needs batch sums");
+    bn_prepare_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sums, groups, C, (double)count_per_group, gamma, beta, running_mean,
+                                                       running_var, momentum, eps, training, saved);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_bn_apply(const float* y, const float* saved, const float* residual, float* z, long long rows, int C,
+                              int groups, int relu, void* stream) {
+    SCSFM_CHECK_ARG(y && saved && z && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 && rows % groups == 0, "bn_apply: bad arguments");
+    bn_apply_kernel<<<grid_for(rows * (C / 4)), NT, 0, ST>>>(y, saved, residual, z, rows, C, rows / groups, relu);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y, const float* saved, const float* gamma,
+                                 float* dy, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
+                                 int relu, double* work, void* stream) {
+    (void)gamma;
+    SCSFM_CHECK_ARG(dz && y && saved && dy && work && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 && rows % groups == 0,
+                    "bn_backward: bad arguments");
+    SCSFM_CHECK_ARG(!relu || z, "bn_backward: relu gate needs z");
+    const long long rpg = rows / groups;
+    SCSFM_CHECK_CUDA(cudaMemsetAsync(work, 0, (size_t)groups * C * 2 * sizeof(double), ST));
+    int chunks = (int)((rpg + 1023) / 1024);
+    if (chunks > 296) chunks = 296;
+    const int rpc = (int)((rpg + chunks - 1) / chunks);
+    bn_bwd_reduce_kernel<<<dim3((unsigned)((rpg + rpc - 1) / rpc), groups, (C + 63) / 64), NT, 0, ST>>>(dz, z, y, saved, rpg, C, relu, rpc, work);
+    SCSFM_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<<<grid_for(rows * (C / 4)), NT, 0, ST>>>(dz, z, y, saved, work, dy, dres, rows, C, rpg, relu);
+    SCSFM_CHECK_LAUNCH();
+    if (dgamma || dbeta) {
+        bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST>>>(work, groups, C, dgamma, dbeta);
+        SCSFM_CHECK_LAUNCH();
+    }
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_maxpool_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* idx, void* stream) {
+    SCSFM_CHECK_ARG(x && y && idx && B > 0 && H > 1 && W > 1 && C > 0 && (C & 3) == 0, "maxpool_fwd: bad arguments");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    maxpool_fwd_kernel<<<grid_for((long long)B * Ho * Wo * (C / 4)), NT, 0, ST>>>(x, B, H, W, C, Ho, Wo, y, idx);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_maxpool_bwd(const float* dy, const unsigned char* idx, int B, int H, int W, int C, float* dx, int accumulate,
+                                 void* stream) {
+    SCSFM_CHECK_ARG(dy && idx && dx && B > 0 && H > 1 && W > 1 && C > 0 && (C & 3) == 0, "maxpool_bwd: bad arguments");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    maxpool_bwd_kernel<<<grid_for((long long)B * H * W * (C / 4)), NT, 0, ST>>>(dy, idx, B, H, W, C, Ho, Wo, dx, accumulate);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_upcat_fwd(const float* lo, const float* skip, int B, int H, int W, int C1, int C2, float* out, void* stream) {
+    SCSFM_CHECK_ARG(lo && out && B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0 && C1 > 0 && (C1 & 3) == 0 && C2 >= 0 &&
+                        (C2 & 3) == 0 && (C2 == 0 || skip), "upcat_fwd: bad arguments");
+    upcat_fwd_kernel<<<grid_for((long long)B * H * W * ((C1 + C2) / 4)), NT, 0, ST>>>(lo, skip, B, H, W, C1, C2, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_fold_bwd(const float* dpad, int B, int H, int W, int C1, int C2, int upsample, float* d_lo,
+                              const float* lo_act, int act, int accumulate, float* d_skip, void* stream) {
+    SCSFM_CHECK_ARG(dpad && d_lo && B > 0 && H >= 2 && W >= 2 && C1 > 0 && (C1 & 3) == 0 && C2 >= 0 && (C2 & 3) == 0, "fold_bwd: bad arguments");
+    SCSFM_CHECK_ARG(act == ACT_NONE || lo_act, "fold_bwd: activation gradient needs the activation output");
+    if (!upsample) {
+        SCSFM_CHECK_ARG(C2 == 0, "fold_bwd: concat without upsample is not used by the decoder");
+        fold_plain_kernel<<<grid_for((long long)B * H * W * (C1 / 4)), NT, 0, ST>>>(dpad, B, H, W, C1, d_lo, lo_act, act, accumulate);
+        SCSFM_CHECK_LAUNCH();
+        return SCSFM_OK;
+    }
+    SCSFM_CHECK_ARG((H & 1) == 0 && (W & 1) == 0 && (C2 == 0 || d_skip), "fold_bwd: bad upsample geometry");
+    fold_up_lo_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C1 / 4)), NT, 0, ST>>>(dpad, B, H, W, C1, C1 + C2, d_lo, lo_act, act);
+    SCSFM_CHECK_LAUNCH();
+    if (C2 > 0) {
+        fold_up_skip_kernel<<<grid_for((long long)B * H * W * (C2 / 4)), NT, 0, ST>>>(dpad, B, H, W, C1, C2, d_skip);
+        SCSFM_CHECK_LAUNCH();
+    }
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_act_bwd(float* d, const float* out, long long n, int act, void* stream) {
+    SCSFM_CHECK_ARG(d && out && n > 0, "act_bwd: bad arguments");
+    act_bwd_kernel<<<grid_for(n), NT, 0, ST>>>(d, out, n, act);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, float scale, float* out, void* stream) {
+    SCSFM_CHECK_ARG(x && out && B > 0 && HW > 0 && C > 0, "spatial_mean_fwd: bad arguments");
+    spatial_mean_fwd_kernel<<<B * C, NT, 0, ST>>>(x, HW, C, scale, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream) {
+    SCSFM_CHECK_ARG(dout && dx && B > 0 && HW > 0 && C > 0, "spatial_mean_bwd: bad arguments");
+    spatial_mean_bwd_kernel<<<grid_for((long long)B * HW * C), NT, 0, ST>>>(dout, B, HW, C, scale, dx);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+    SCSFM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}

@@ -87,3 +87,23 @@ def dev_f32(t, name):
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32, got %s" % (name, t.dtype))
     return t.contiguous()
+
+
+# ----- launch accounting / optional per-family CUDA-event profiling (used by bench.py) -------------
+STATS = {"launches": 0}
+PROF = {"enabled": False, "only": None, "events": []}
+
+
+def launch(fn, what, family, n_kernels, work, *args):
+    """Call a C-ABI entry point; count its kernel launches; optionally bracket it with CUDA events on the
+    launching stream.  `work` = algorithmic FLOPs (convs) or bytes (HBM-bound ops) of the call."""
+    STATS["launches"] += n_kernels
+    if PROF["enabled"] and (PROF["only"] is None or family in PROF["only"]):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROF["events"].append((family, work, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, what)

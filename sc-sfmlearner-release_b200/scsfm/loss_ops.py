@@ -94,8 +94,8 @@ class PhotoGeoLoss(torch.autograd.Function):
             st = torch.empty(lib.scsfm_pairwise_stats_bytes(len(chunk), B) // 8, device=tgt_img.device,
                              dtype=torch.float64)
             arr = (L.PairJob * len(chunk))(*chunk)
-            L.check(lib.scsfm_pairwise_fwd(arr, len(chunk), L.ptr(intrinsics), B, H, W, flags, padding, L.ptr(st),
-                                           L.ptr(part), None, L.stream()), "scsfm_pairwise_fwd")
+            L.launch(lib.scsfm_pairwise_fwd, "scsfm_pairwise_fwd", "pair_fwd", 2, 32.0 * len(chunk) * B * H * W, arr, len(chunk),
+                     L.ptr(intrinsics), B, H, W, flags, padding, L.ptr(st), L.ptr(part), None, L.stream())
             out = out + part if len(jobs) > L.MAX_JOBS else part
             stats.append(st)
         ctx.cfg = cfg
@@ -124,8 +124,8 @@ class PhotoGeoLoss(torch.autograd.Function):
         for k, c0 in enumerate(range(0, len(jobs), L.MAX_JOBS)):
             chunk = jobs[c0:c0 + L.MAX_JOBS]
             arr = (L.PairJob * len(chunk))(*chunk)
-            L.check(lib.scsfm_pairwise_bwd(arr, len(chunk), L.ptr(intrinsics), B, H, W, flags, padding,
-                                           L.ptr(ctx.stats[k]), L.ptr(gout), L.stream()), "scsfm_pairwise_bwd")
+            L.launch(lib.scsfm_pairwise_bwd, "scsfm_pairwise_bwd", "pair_bwd", 2, 44.0 * len(chunk) * B * H * W, arr, len(chunk),
+                     L.ptr(intrinsics), B, H, W, flags, padding, L.ptr(ctx.stats[k]), L.ptr(gout), L.stream())
         return (None, None, None) + tuple(grads.get(k) if k is not None else None for k in order)
 
 
@@ -189,7 +189,8 @@ class SmoothLoss(torch.autograd.Function):
                                    for i in range(n)])
         st = torch.empty(lib.scsfm_smooth_stats_bytes(n, B) // 8, device=tensors[0].device, dtype=torch.float64)
         out = torch.empty(1, device=tensors[0].device, dtype=torch.float32)
-        L.check(lib.scsfm_smooth_fwd(jobs, n, B, H, W, L.ptr(st), L.ptr(out), L.stream()), "scsfm_smooth_fwd")
+        L.launch(lib.scsfm_smooth_fwd, "scsfm_smooth_fwd", "smooth_fwd", 3, 16.0 * n * B * H * W, jobs, n, B, H, W, L.ptr(st), L.ptr(out),
+                 L.stream())
         ctx.n, ctx.stats = n, st
         ctx.save_for_backward(*tensors)
         return out[0]
@@ -205,7 +206,8 @@ class SmoothLoss(torch.autograd.Function):
         jobs = (L.SmoothJob * n)(*[L.SmoothJob(L.ptr(tensors[2 * i]), L.ptr(tensors[2 * i + 1]), L.ptr(grads[i]))
                                    for i in range(n)])
         gout = g.reshape(1).to(torch.float32).contiguous()
-        L.check(lib.scsfm_smooth_bwd(jobs, n, B, H, W, L.ptr(ctx.stats), L.ptr(gout), L.stream()), "scsfm_smooth_bwd")
+        L.launch(lib.scsfm_smooth_bwd, "scsfm_smooth_bwd", "smooth_bwd", 1, 20.0 * n * B * H * W, jobs, n, B, H, W, L.ptr(ctx.stats),
+                 L.ptr(gout), L.stream())
         out = [None]
         for i in range(n):
             out += [grads[i], None]

@@ -1,0 +1,231 @@
+"""Thin Python layer over the network entry points of libscsfm (include/scsfm.h, "Network operators").
+
+Tensors are torch CUDA tensors used as typed device buffers: activations NHWC `[B,H,W,C]` fp32
+contiguous, conv weights `[Cout,kh,kw,Cin]`.  Every function enqueues on torch's current stream.
+"""
+import ctypes
+
+import torch
+
+from . import lib as L
+
+PAD_ZERO, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_ELU, ACT_DISP = 0, 1, 2, 3
+
+# "fp32": exact CUDA-core kernels everywhere (parity mode).  "tf32": tcgen05 tensor-core kernels on the
+# layers they support (same arithmetic class as the reference's cuDNN TF32 default on GPU).
+CONFIG = {"conv_mode": "fp32"}
+
+
+class Conv(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("inp", "w", "bias", "out", "dout", "din", "addend", "dw", "dbias",
+                                                "bn_sums")] +
+                [(n, ctypes.c_int) for n in ("bn_groups", "B", "Hi", "Wi", "Cin", "Ho", "Wo", "Cout", "kh", "kw",
+                                             "stride", "pad", "pad_mode", "act")])
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = L.load()
+    if not _bound:
+        I, P, LL, F = ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float
+        CP = ctypes.POINTER(Conv)
+        for name in ("scsfm_conv2d_fwd_simt", "scsfm_conv2d_dgrad_simt", "scsfm_conv2d_wgrad_simt",
+                     "scsfm_conv2d_fwd_tc", "scsfm_conv2d_dgrad_tc", "scsfm_conv2d_wgrad_tc"):
+            if hasattr(lib, name):
+                getattr(lib, name).argtypes = [CP, P]
+        lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
+        lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
+        lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
+        lib.scsfm_bn_apply.argtypes = [P, P, P, P, LL, I, I, I, P]
+        lib.scsfm_bn_backward.argtypes = [P, P, P, P, P, P, P, P, P, LL, I, I, I, P, P]
+        lib.scsfm_maxpool_fwd.argtypes = [P, I, I, I, I, P, P, P]
+        lib.scsfm_maxpool_bwd.argtypes = [P, P, I, I, I, I, P, I, P]
+        lib.scsfm_upcat_fwd.argtypes = [P, P, I, I, I, I, I, P, P]
+        lib.scsfm_fold_bwd.argtypes = [P, I, I, I, I, I, I, P, P, I, I, P, P]
+        lib.scsfm_act_bwd.argtypes = [P, P, LL, I, P]
+        lib.scsfm_spatial_mean_fwd.argtypes = [P, I, I, I, F, P, P]
+        lib.scsfm_spatial_mean_bwd.argtypes = [P, I, I, I, F, P, P]
+        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P]
+        _bound = True
+    return lib
+
+
+def empty(shape, like):
+    return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+
+def _use_tc(kind, Cin, Cout, kh, stride):
+    if CONFIG["conv_mode"] != "tf32":
+        return False
+    lib = _lib()
+    return hasattr(lib, "scsfm_conv2d_%s_tc" % kind) and tc_supported(kind, Cin, Cout, kh, stride)
+
+
+def tc_supported(kind, Cin, Cout, kh, stride):
+    """Shapes the tcgen05 kernels take; everything else runs the CUDA-core kernel."""
+    return False
+
+
+def conv_desc(x_shape, w, stride, pad, pad_mode, act):
+    B, Hi, Wi, Cin = x_shape
+    Cout, kh, kw, _ = w.shape
+    Ho = (Hi + 2 * pad - kh) // stride + 1
+    Wo = (Wi + 2 * pad - kw) // stride + 1
+    return Conv(None, L.ptr(w), None, None, None, None, None, None, None, None, 1, B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw,
+                stride, pad, pad_mode, act)
+
+
+def _flops(d):
+    """Algorithmic FLOPs of one conv pass: 2 * (B*Ho*Wo) * Cout * (kh*kw*Cin)."""
+    return 2.0 * d.B * d.Ho * d.Wo * d.Cout * d.kh * d.kw * d.Cin
+
+
+def conv_fwd(x, w, bias=None, stride=1, pad=0, pad_mode=PAD_ZERO, act=ACT_NONE, bn_sums=None, bn_groups=1):
+    """y = act(conv(x, w) + bias); optionally accumulates per-(group, channel) sum / sum-of-squares of y."""
+    lib = _lib()
+    d = conv_desc(x.shape, w, stride, pad, pad_mode, act)
+    y = empty((d.B, d.Ho, d.Wo, d.Cout), x)
+    d.inp, d.bias, d.out, d.bn_sums, d.bn_groups = x.data_ptr(), bias.data_ptr() if bias is not None else None, \
+        y.data_ptr(), bn_sums.data_ptr() if bn_sums is not None else None, bn_groups
+    tc = _use_tc("fwd", d.Cin, d.Cout, d.kh, stride)
+    fn = lib.scsfm_conv2d_fwd_tc if tc else lib.scsfm_conv2d_fwd_simt
+    L.launch(fn, "scsfm_conv2d_fwd", "conv_fwd_tc" if tc else "conv_fwd_simt", 1, _flops(d), ctypes.byref(d), L.stream())
+    return y
+
+
+def conv_dgrad(dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=False):
+    """Gradient w.r.t. the conv input.  padded_input=True returns the gradient of the reflect-PADDED input
+    ([B,H+2,W+2,C], to be folded by fold_bwd) for a pad-1 reflection conv."""
+    lib = _lib()
+    B, Hi, Wi, Cin = x_shape
+    if padded_input:
+        Hi, Wi, pad = Hi + 2, Wi + 2, 0
+    d = conv_desc((B, Hi, Wi, Cin), w, stride, pad, PAD_ZERO, ACT_NONE)
+    assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:]), (d.Ho, d.Wo, d.Cout, dout.shape)
+    din = empty((B, Hi, Wi, Cin), dout)
+    d.dout, d.din, d.addend = dout.data_ptr(), din.data_ptr(), addend.data_ptr() if addend is not None else None
+    tc = _use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
+    fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
+    L.launch(fn, "scsfm_conv2d_dgrad", "conv_dgrad_tc" if tc else "conv_dgrad_simt", 1, _flops(d), ctypes.byref(d), L.stream())
+    return din
+
+
+def conv_wgrad(x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
+    """dw += dout^T * gather(x); dbias += column sums of dout."""
+    lib = _lib()
+    d = conv_desc(x.shape, dw, stride, pad, pad_mode, ACT_NONE)
+    assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:])
+    d.inp, d.dout, d.dw, d.dbias = x.data_ptr(), dout.data_ptr(), dw.data_ptr(), dbias.data_ptr() if dbias is not None else None
+    d.w = None
+    tc = _use_tc("wgrad", d.Cin, d.Cout, d.kh, stride)
+    fn = lib.scsfm_conv2d_wgrad_tc if tc else lib.scsfm_conv2d_wgrad_simt
+    L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
+             ctypes.byref(d), L.stream())
+
+
+def nchw_to_nhwc(a, b=None):
+    B, C, H, W = a.shape
+    out = empty((B, H, W, C * (2 if b is not None else 1)), a)
+    L.launch(_lib().scsfm_nchw_to_nhwc, "scsfm_nchw_to_nhwc", "layout", 1, 8.0 * out.numel(), L.ptr(a), L.ptr(b), B, C, H, W, L.ptr(out), L.stream())
+    return out
+
+
+def nhwc_to_nchw(x):
+    B, H, W, C = x.shape
+    out = empty((B, C, H, W), x)
+    L.launch(_lib().scsfm_nhwc_to_nchw, "scsfm_nhwc_to_nchw", "layout", 1, 8.0 * out.numel(), L.ptr(x), B, C, H, W, L.ptr(out), L.stream())
+    return out
+
+
+def bn_prepare(sums, groups, count, gamma, beta, rmean, rvar, momentum, eps, training):
+    C = gamma.numel()
+    saved = empty((groups, C, 4), gamma)
+    L.launch(_lib().scsfm_bn_prepare, "scsfm_bn_prepare", "bn_prepare", 1, 0.0, L.ptr(sums), groups, C, count, L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar),
+                                    momentum, eps, 1 if training else 0, L.ptr(saved), L.stream())
+    return saved
+
+
+def bn_apply(y, saved, residual, relu, groups=1):
+    z = torch.empty_like(y)
+    rows = y.numel() // y.shape[-1]
+    L.launch(_lib().scsfm_bn_apply, "scsfm_bn_apply", "bn_apply", 1, (12.0 if residual is not None else 8.0) * y.numel(), L.ptr(y), L.ptr(saved), L.ptr(residual), L.ptr(z), rows, y.shape[-1], groups,
+                                  1 if relu else 0, L.stream())
+    return z
+
+
+def bn_backward(dz, z, y, saved, dgamma, dbeta, relu, want_dres, groups=1):
+    """Returns (dy, dres).  dres (= dz gated by the ReLU) is written in place over dz when requested."""
+    C = y.shape[-1]
+    rows = y.numel() // C
+    dy = torch.empty_like(y)
+    work = torch.empty(groups * C * 2, device=y.device, dtype=torch.float64)
+    dres = dz if want_dres else None
+    L.launch(_lib().scsfm_bn_backward, "scsfm_bn_backward", "bn_bwd", 4, 28.0 * y.numel(), L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(saved), None, L.ptr(dy), L.ptr(dres), L.ptr(dgamma),
+                                     L.ptr(dbeta), rows, C, groups, 1 if relu else 0, L.ptr(work), L.stream())
+    return dy, dres
+
+
+def maxpool_fwd(x):
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = empty((B, Ho, Wo, C), x)
+    idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+    L.launch(_lib().scsfm_maxpool_fwd, "scsfm_maxpool_fwd", "pool", 1, 4.0 * x.numel(), L.ptr(x), B, H, W, C, L.ptr(y), L.ptr(idx), L.stream())
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, x_shape, dx, accumulate):
+    B, H, W, C = x_shape
+    L.launch(_lib().scsfm_maxpool_bwd, "scsfm_maxpool_bwd", "pool", 1, 4.0 * dx.numel(), L.ptr(dy), L.ptr(idx), B, H, W, C, L.ptr(dx), 1 if accumulate else 0, L.stream())
+
+
+def upcat_fwd(lo, skip):
+    B, h, w, C1 = lo.shape
+    C2 = skip.shape[-1] if skip is not None else 0
+    out = empty((B, 2 * h, 2 * w, C1 + C2), lo)
+    L.launch(_lib().scsfm_upcat_fwd, "scsfm_upcat_fwd", "upcat", 1, 8.0 * out.numel(), L.ptr(lo), L.ptr(skip), B, 2 * h, 2 * w, C1, C2, L.ptr(out), L.stream())
+    return out
+
+
+def fold_plain(dpad, d, act_out, act, accumulate):
+    B, Hp, Wp, C = dpad.shape
+    L.launch(_lib().scsfm_fold_bwd, "scsfm_fold_bwd", "fold", 1, 8.0 * d.numel(), L.ptr(dpad), B, Hp - 2, Wp - 2, C, 0, 0, L.ptr(d),
+             L.ptr(act_out), act, 1 if accumulate else 0, None, L.stream())
+
+
+def fold_upcat(dpad, C1, lo_act, act):
+    B, Hp, Wp, Ct = dpad.shape
+    H, W, C2 = Hp - 2, Wp - 2, Ct - C1
+    d_lo = empty((B, H // 2, W // 2, C1), dpad)
+    d_skip = empty((B, H, W, C2), dpad) if C2 > 0 else None
+    L.launch(_lib().scsfm_fold_bwd, "scsfm_fold_bwd", "fold", 2 if C2 > 0 else 1, 4.0 * dpad.numel(), L.ptr(dpad), B, H, W, C1, C2, 1,
+             L.ptr(d_lo), L.ptr(lo_act), act, 0, L.ptr(d_skip), L.stream())
+    return d_lo, d_skip
+
+
+def act_bwd_(d, out, act):
+    L.launch(_lib().scsfm_act_bwd, "scsfm_act_bwd", "elementwise", 1, 12.0 * d.numel(), L.ptr(d), L.ptr(out), d.numel(), act, L.stream())
+    return d
+
+
+def spatial_mean_fwd(x, scale):
+    B, H, W, C = x.shape
+    out = empty((B, C), x)
+    L.launch(_lib().scsfm_spatial_mean_fwd, "scsfm_spatial_mean_fwd", "pose_head", 1, 4.0 * x.numel(), L.ptr(x), B, H * W, C, scale, L.ptr(out), L.stream())
+    return out
+
+
+def spatial_mean_bwd(dout, x_shape, scale):
+    B, H, W, C = x_shape
+    dx = empty(x_shape, dout)
+    L.launch(_lib().scsfm_spatial_mean_bwd, "scsfm_spatial_mean_bwd", "pose_head", 1, 4.0 * dx.numel(), L.ptr(dout), B, H * W, C, scale, L.ptr(dx), L.stream())
+    return dx
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, 28.0 * param.numel(), L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr, beta1,
+                                   beta2, eps, weight_decay, step, L.stream())

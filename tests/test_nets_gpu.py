@@ -1,0 +1,276 @@
+"""Parity of the network kernels (conv fwd/dgrad/wgrad, BN, pool, decoder ops) and of the whole
+DispResNet / PoseResNet forward+backward against the oracle and the reference vectors.  Needs a GPU.
+
+fp32 CUDA-core mode ("fp32"): same arithmetic class as the CPU reference -> tolerances are fp32 noise.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from golden_util import det_image, det_weights
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from scsfm import nnops
+    return nnops
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad, pad_mode(0 zero/1 reflect), act, bias
+    (2, 20, 28, 3, 64, 7, 2, 3, 0, 0, False),     # stem
+    (2, 20, 28, 6, 64, 7, 2, 3, 0, 0, False),     # pose stem
+    (2, 12, 20, 64, 64, 3, 1, 1, 0, 0, False),    # layer1
+    (2, 12, 20, 64, 128, 3, 2, 1, 0, 0, False),   # layer2.0.conv1
+    (2, 12, 20, 64, 128, 1, 2, 0, 0, 0, False),   # downsample
+    (1, 9, 13, 32, 16, 3, 1, 1, 1, 2, True),      # decoder reflect + ELU, Cout 16
+    (1, 10, 14, 96, 32, 3, 1, 1, 1, 2, True),     # decoder, Cout 32
+    (2, 10, 14, 16, 1, 3, 1, 1, 1, 3, True),      # dispconv + sigmoid
+    (2, 4, 6, 256, 6, 1, 1, 0, 0, 0, True),       # pose head
+    (2, 4, 6, 512, 256, 1, 1, 0, 0, 1, True),     # pose squeeze + ReLU
+    (1, 7, 9, 256, 64, 1, 1, 0, 0, 0, False),     # bottleneck 1x1
+]
+
+
+def _ref_conv(x, w, b, stride, pad, pad_mode, act):
+    if pad_mode == 1:
+        x = F.pad(x, (pad, pad, pad, pad), mode="reflect")
+        pad = 0
+    y = F.conv2d(x, w, b, stride, pad)
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
+        y = F.elu(y)
+    elif act == 3:
+        y = 10 * torch.sigmoid(y) + 0.01
+    return y
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad_vs_torch_fp64(case):
+    O = _ops()
+    B, H, W, Cin, Cout, k, stride, pad, pad_mode, act, bias = case
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g, dtype=torch.float64) / (Cin * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g, dtype=torch.float64).requires_grad_(True) if bias else None
+    pre = _ref_conv(x, w, b, stride, pad, pad_mode, 0)
+    y = _ref_conv(x, w, b, stride, pad, pad_mode, act)
+    dpre = torch.randn(pre.shape, generator=g, dtype=torch.float64)
+    pre.backward(dpre)
+
+    xc = x.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    wc = w.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    bc = b.detach().float().to(DEV) if bias else None
+    sums = torch.zeros(Cout * 2, device=DEV, dtype=torch.float64)
+    yc = O.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1)
+    assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < 2e-6
+    s = sums.view(Cout, 2).cpu()
+    np.testing.assert_allclose(s[:, 0], y.detach().sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(s[:, 1], (y.detach() ** 2).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+    dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    dw = torch.zeros_like(wc)
+    db = torch.zeros(Cout, device=DEV) if bias else None
+    O.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
+    assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 2e-6
+    if bias:
+        assert rel_l2(db, b.grad) < 2e-6
+    if pad_mode == 0:
+        add = torch.randn(B, H, W, Cin, generator=g).to(DEV)
+        dx = O.conv_dgrad(dc, wc, xc.shape, stride, pad, add)
+        assert rel_l2((dx - add).permute(0, 3, 1, 2), x.grad) < 2e-6
+    else:
+        dpad = O.conv_dgrad(dc, wc, xc.shape, stride, pad, None, padded_input=True)
+        dx = torch.zeros_like(xc)
+        O.fold_plain(dpad, dx, None, O.ACT_NONE, accumulate=False)
+        assert rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 2e-6
+
+
+def test_bn_pool_upcat_ops_vs_torch():
+    O = _ops()
+    g = torch.Generator().manual_seed(3)
+    B, H, W, C = 3, 10, 14, 32
+    y = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    res = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g, dtype=torch.float64)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, generator=g, dtype=torch.float64)).requires_grad_(True)
+    rm, rv = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    z = F.relu(F.batch_norm(y, rm, rv, gamma, beta, True, 0.1, 1e-5) + res)
+    dz = torch.randn(z.shape, generator=g, dtype=torch.float64)
+    z.backward(dz)
+    nh = lambda t: t.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)  # noqa: E731
+    yc, rc = nh(y), nh(res)
+    sums = torch.stack([yc.double().sum((0, 1, 2)), (yc.double() ** 2).sum((0, 1, 2))], 1).reshape(-1).contiguous()
+    gm, bt = gamma.detach().float().to(DEV), beta.detach().float().to(DEV)
+    rmc, rvc = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    saved = O.bn_prepare(sums, 1, B * H * W, gm, bt, rmc, rvc, 0.1, 1e-5, True)
+    zc = O.bn_apply(yc, saved, rc, True)
+    assert rel_l2(zc.permute(0, 3, 1, 2), z.detach()) < 2e-6
+    assert rel_l2(rmc, rm) < 1e-5 and rel_l2(rvc, rv) < 1e-5
+    dgm, dbt = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dzc = nh(dz)
+    dy, dres = O.bn_backward(dzc, zc, yc, saved, dgm, dbt, True, True)
+    assert rel_l2(dy.permute(0, 3, 1, 2), y.grad) < 1e-5
+    assert rel_l2(dres.permute(0, 3, 1, 2), res.grad) < 1e-6
+    assert rel_l2(dgm, gamma.grad) < 1e-5 and rel_l2(dbt, beta.grad) < 1e-5
+    # eval mode uses the running statistics
+    saved_e = O.bn_prepare(None, 1, 0, gm, bt, rmc, rvc, 0.1, 1e-5, False)
+    ze = O.bn_apply(yc, saved_e, None, False)
+    want = F.batch_norm(y.detach(), rm, rv, gamma.detach(), beta.detach(), False, 0.1, 1e-5)
+    assert rel_l2(ze.permute(0, 3, 1, 2), want) < 2e-6
+
+    # max-pool 3x3/2 pad 1 (odd sizes too)
+    for (h, w) in ((10, 14), (9, 13)):
+        x = torch.randn(2, 8, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+        p = F.max_pool2d(x, 3, 2, 1)
+        dp = torch.randn(p.shape, generator=g, dtype=torch.float64)
+        p.backward(dp)
+        xc = nh(x)
+        pc, idx = O.maxpool_fwd(xc)
+        assert rel_l2(pc.permute(0, 3, 1, 2), p.detach()) < 1e-6
+        dx = torch.ones_like(xc)
+        O.maxpool_bwd(nh(dp), idx, xc.shape, dx, True)
+        assert rel_l2((dx - 1).permute(0, 3, 1, 2), x.grad) < 1e-6
+
+    # upsample + concat, forward and (through a reflect-pad conv's padded gradient) backward
+    lo = torch.randn(2, 8, 5, 7, generator=g, dtype=torch.float64, requires_grad=True)
+    sk = torch.randn(2, 12, 10, 14, generator=g, dtype=torch.float64, requires_grad=True)
+    a = F.elu(lo)
+    cat = torch.cat([F.interpolate(a, scale_factor=2, mode="nearest"), sk], 1)
+    padded = F.pad(cat, (1, 1, 1, 1), mode="reflect")
+    dpad = torch.randn(padded.shape, generator=g, dtype=torch.float64)
+    padded.backward(dpad)
+    ac = nh(a)
+    catc = O.upcat_fwd(ac, nh(sk))
+    assert rel_l2(catc.permute(0, 3, 1, 2), cat.detach()) < 1e-6
+    d_lo, d_sk = O.fold_upcat(nh(dpad), 8, ac, O.ACT_ELU)
+    assert rel_l2(d_lo.permute(0, 3, 1, 2), lo.grad) < 1e-6
+    assert rel_l2(d_sk.permute(0, 3, 1, 2), sk.grad) < 1e-6
+
+
+def _build(kind, layers):
+    import models
+    net = models.DispResNet(layers, False) if kind == "disp" else models.PoseResNet(layers, False)
+    net.load_state_dict(det_weights(net.state_dict()))
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("layers", [18, 50])
+@pytest.mark.parametrize("kind", ["disp", "pose"])
+def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind):
+    """Train-mode forward, backward (every parameter gradient), BN running stats and eval-mode forward."""
+    from oracle import nets as N
+    g = golden_nets
+    tag = f"{kind}{layers}"
+    net = _build(kind, layers)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(g[f"{tag}_keys"])
+    net.train()
+    img1, img2 = det_image("img1", 2, 64, 96), det_image("img2", 2, 64, 96)
+    if kind == "disp":
+        outs = net(img1.to(DEV))
+        assert isinstance(outs, list) and len(outs) == 4
+        loss = sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(outs))
+        for s, o in enumerate(outs):
+            np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"{tag}_out_s{s}"], rtol=5e-4, atol=5e-5)
+    else:
+        o = net(img1.to(DEV), img2.to(DEV))
+        loss = (o * torch.arange(1, 7, dtype=o.dtype, device=DEV)).sum() * 100
+        np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"{tag}_out"], rtol=1e-3, atol=2e-7)
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), g[f"{tag}_loss"][0], rtol=2e-5)
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    names = list(g[f"{tag}_grad_names"])
+    norms = np.array([float(grads[k].double().norm()) for k in names])
+    np.testing.assert_allclose(norms, g[f"{tag}_grad_norms"], rtol=2e-2, atol=1e-8)
+    # parameters the reference leaves without gradient (fc head) stay exactly zero here
+    for k, v in grads.items():
+        if k not in names:
+            assert float(v.abs().max()) == 0.0, k
+    # element-wise gradients against the fp64 oracle run on the same weights
+    ref = (N.DispResNet(layers) if kind == "disp" else N.PoseResNet(layers)).double()
+    ref.load_state_dict({k: v.double() for k, v in det_weights(ref.state_dict()).items()})
+    ref.train()
+    if kind == "disp":
+        ro = ref(img1.double())
+        rl = sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(ro))
+    else:
+        ro = ref(img1.double(), img2.double())
+        rl = (ro * torch.arange(1, 7, dtype=ro.dtype)).sum() * 100
+    rl.backward()
+    worst = 0.0
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        e = rel_l2(grads[k], p.grad)
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+    print(tag, "worst per-parameter gradient rel-L2 vs fp64 oracle: %.2e" % worst)
+    sd2 = net.state_dict()
+    rn = np.array([float(sd2[k].double().norm()) for k in g[f"{tag}_running_names"]])
+    np.testing.assert_allclose(rn, g[f"{tag}_running_norms"], rtol=1e-4)
+    net.eval()
+    with torch.no_grad():
+        e = net(img1.to(DEV)) if kind == "disp" else net(img1.to(DEV), img2.to(DEV))
+    assert torch.is_tensor(e)
+    np.testing.assert_allclose(e.cpu().numpy(), g[f"{tag}_eval_out"], rtol=5e-4, atol=5e-5)
+
+
+def test_state_dict_roundtrip_and_gradient_accumulation():
+    import models
+    net = models.DispResNet(18, False).to(DEV)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net2 = models.DispResNet(18, False).to(DEV)
+    net2.load_state_dict(sd)
+    x = det_image("img1", 1, 64, 96).to(DEV)
+    net.train(); net2.train()
+    a, b = net(x)[0], net2(x)[0]
+    assert torch.equal(a, b)
+    # two backward passes accumulate; zero_grad resets
+    (a.mean()).backward()
+    g1 = net.flat_grads().clone()
+    (net(x)[0].mean()).backward()
+    assert rel_l2(net.flat_grads(), 2 * g1) < 1e-4
+    net.zero_grad()
+    assert float(net.flat_grads().abs().max()) == 0.0
+    # a torch optimizer that drops gradients (set_to_none) is handled too
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    opt.zero_grad(set_to_none=True)
+    (net(x)[0].mean()).backward()
+    assert rel_l2(net.flat_grads(), g1) < 1e-4
+    assert all(p.grad is not None for p in net.parameters())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        models.PoseResNet(18, False)(x.cpu(), x.cpu())
+
+
+def test_arena_adam_matches_torch_adam():
+    from oracle import nets as N
+    from scsfm.nets import ArenaAdam
+    import models
+    net = models.PoseResNet(18, False)
+    net.load_state_dict(det_weights(net.state_dict()))
+    net = net.to(DEV)
+    ref = N.PoseResNet(18)
+    ref.load_state_dict(det_weights(ref.state_dict()))
+    ref = ref.to(DEV)
+    opt = ArenaAdam([net], lr=1e-3)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    x1, x2 = det_image("img1", 2, 64, 96).to(DEV), det_image("img2", 2, 64, 96).to(DEV)
+    net.train(); ref.train()
+    torch.backends.cudnn.allow_tf32 = False
+    for _ in range(3):
+        opt.zero_grad()
+        (net(x1, x2).sum() * 100).backward()
+        opt.step()
+        ropt.zero_grad()
+        (ref(x1, x2).sum() * 100).backward()
+        ropt.step()
+    rsd = ref.state_dict()
+    for k, v in net.state_dict().items():
+        if v.dtype == torch.float32 and "fc." not in k:
+            assert rel_l2(v, rsd[k]) < 2e-3, k

@@ -130,3 +130,20 @@ def test_networks(golden_nets, layers, kind):
     with torch.no_grad():
         e = net(img1) if kind == "disp" else net(img1, img2)
     np.testing.assert_allclose(e.numpy(), g[f"{tag}_eval_out"], rtol=2e-4, atol=2e-5)
+
+
+def test_library_kernel_mode_agrees_with_the_restatement(golden_warp):
+    """bench.py times the oracle with F.grid_sample / F.avg_pool2d switched in; both forms must agree."""
+    g = golden_warp
+    vals = []
+    for fast in (False, True):
+        G.USE_LIBRARY_KERNELS = fast
+        try:
+            tgt, refs, K, td, rd, ps, pi = golden_loss_inputs(g, requires_grad=True)
+            p, q = L.compute_photo_and_geometry_loss(tgt, refs, K, td, rd, ps, pi, 2, 1, 1, 1, "zeros")
+            (p + 0.5 * q).backward()
+            vals.append((float(p.detach()), float(q.detach()), td[0].grad.clone(), ps[0].grad.clone()))
+        finally:
+            G.USE_LIBRARY_KERNELS = False
+    np.testing.assert_allclose(vals[0][:2], vals[1][:2], rtol=2e-6)
+    assert rel_l2(vals[0][2], vals[1][2]) < 1e-4 and rel_l2(vals[0][3], vals[1][3]) < 1e-3

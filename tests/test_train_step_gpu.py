@@ -1,0 +1,73 @@
+"""Whole optimisation step (train.py:259-282): CUDA path vs the oracle's train_step on identical
+weights and inputs.  Needs a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import det_weights
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_two_training_steps_match_the_oracle():
+    import models
+    from oracle import nets as N
+    from oracle import step as OS
+    from scsfm import synth
+    from scsfm.trainer import Trainer
+    B, H, W = 2, 96, 160
+    tgt, refs, K = synth.triplet(5, B, H, W)
+    disp, pose = models.DispResNet(18, False), models.PoseResNet(18, False)
+    odisp, opose = N.DispResNet(18), N.PoseResNet(18)
+    for a, b in ((disp, odisp), (pose, opose)):
+        sd = det_weights(b.state_dict())
+        a.load_state_dict(sd)
+        b.load_state_dict(sd)
+    disp, pose = disp.to(DEV).train(), pose.to(DEV).train()
+    odisp.train(); opose.train()
+    tr = Trainer(disp, pose, lr=1e-4, with_auto_mask=0, distributed=False)
+    opt = OS.make_optimizer(odisp, opose, lr=1e-4)
+    c = lambda x: x.to(DEV)  # noqa: E731
+    for it in range(2):
+        got = tr.step(c(tgt), [c(r) for r in refs], c(K))
+        # gradients of this step (before they are zeroed by the next one) for the comparison below
+        g_disp = {k: p.grad.clone() for k, p in disp.named_parameters()}
+        want = OS.train_step(odisp, opose, opt, tgt, refs, K, num_scales=1, with_ssim=1, with_mask=1, with_auto_mask=0)
+        np.testing.assert_allclose([float(v) for v in got], [float(v) for v in want], rtol=2e-4, atol=1e-6)
+        if it == 0:
+            worst = 0.0
+            for k, p in odisp.named_parameters():
+                if p.grad is None:
+                    assert float(g_disp[k].abs().max()) == 0.0
+                    continue
+                e = rel_l2(g_disp[k], p.grad)
+                worst = max(worst, e)
+                assert e < 2e-2, (k, e)
+            print("worst DispResNet parameter-gradient rel-L2 vs fp32 oracle after a full step: %.2e" % worst)
+    # parameters after two Adam updates: elementwise bounded by 2 * lr (Adam's step bound), nearly all identical
+    osd = odisp.state_dict()
+    for k, v in disp.state_dict().items():
+        if v.dtype == torch.float32 and "running" not in k:
+            assert float((v.cpu() - osd[k]).abs().max()) <= 4.1e-4, k
+
+
+def test_step_issues_no_host_synchronisation():
+    """The whole step must be stream-ordered (no .item(), no blocking copies): run it under
+    torch.cuda.set_sync_debug_mode('error')."""
+    import models
+    from scsfm import synth
+    from scsfm.trainer import Trainer
+    tgt, refs, K = synth.triplet(1, 1, 64, 96)
+    tr = Trainer(models.DispResNet(18, False).to(DEV).train(), models.PoseResNet(18, False).to(DEV).train(),
+                 distributed=False)
+    args = (tgt.to(DEV), [r.to(DEV) for r in refs], K.to(DEV))
+    tr.step(*args)          # warm-up: allocations, arena packing
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        tr.step(*args)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
