@@ -138,6 +138,7 @@ int scsfm_smooth_bwd(const ScsfmSmoothJob* jobs_host, int njobs, int B, int H, i
 #define SCSFM_ACT_RELU 1
 #define SCSFM_ACT_ELU 2           /* nn.ELU, DispResNet.py:20 */
 #define SCSFM_ACT_DISP 3          /* 10*sigmoid(x)+0.01, DispResNet.py:98 */
+#define SCSFM_BN_SLOTS 16
 
 typedef struct ScsfmConv {
     /* forward operands */
@@ -151,9 +152,10 @@ typedef struct ScsfmConv {
     const float* addend;  /* optional tensor added to din (residual branch gradient) */
     float* dw;            /* [Cout,kh,kw,Cin], accumulated into (atomic +=) */
     float* dbias;         /* [Cout] or NULL, accumulated into */
-    /* fused BatchNorm statistics of the forward output: sums[g][c] = {sum, sum of squares}, fp64,
-     * accumulated into (caller zeroes).  Samples are split into bn_groups equal groups (one per
-     * network call when several calls are batched into one launch). */
+    /* fused BatchNorm statistics of the forward output: sums[slot][g][c] = {sum, sum of squares}, fp64,
+     * accumulated into (caller zeroes); SCSFM_BN_SLOTS replicas spread the L2 atomic traffic and are added
+     * up by scsfm_bn_prepare.  Samples are split into bn_groups equal groups (one per network call when
+     * several calls are batched into one launch). */
     double* bn_sums;
     int bn_groups;
     int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, pad_mode, act;
@@ -164,12 +166,20 @@ int scsfm_conv2d_fwd_simt(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_dgrad_simt(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
 
+/* tcgen05 (kind::tf32, fp32 accumulation in TMEM) implicit-GEMM convolution; needs Cin % 4 == 0.
+ * dgrad_tc: stride 1 only; p->w must hold the flipped/transposed weights [Cin,kh,kw,Cout] produced by
+ * scsfm_weight_flip (the data gradient is the forward kernel run on dout). */
+int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream);
+int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream);
+int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
+
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
 int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);
 /* NHWC [B,H,W,C] -> NCHW */
 int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, void* stream);
 
 /* BatchNorm2d (torchvision resnet.py blocks): prepare per-channel scale/shift from the fused batch sums
+ * (sums[SCSFM_BN_SLOTS][groups][C][2], see ScsfmConv.bn_sums)
  * (training; updates running stats with `momentum`, unbiased variance) or from the running stats (eval).
  * saved[g][c] = {scale, shift, mean, invstd}. */
 int scsfm_bn_prepare(const double* sums, int groups, int C, long long count_per_group, const float* gamma,

@@ -170,7 +170,8 @@ conv_fwd_simt_kernel(ScsfmConv p) {
 
     // epilogue: bias, activation, store, optional BatchNorm partial sums (per group of samples)
     float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
-    const int rows_per_group = (p.B / (p.bn_groups > 0 ? p.bn_groups : 1)) * p.Ho * p.Wo;
+    const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
+    const int rows_per_group = (p.B / groups) * p.Ho * p.Wo;
     const bool want_stats = p.bn_sums != nullptr;
     const bool uniform_group = want_stats && (m0 / rows_per_group) == ((min(m0 + BM, M) - 1) / rows_per_group);
 #pragma unroll
@@ -188,7 +189,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
                 if (want_stats) {
                     if (uniform_group) { csum[j] += x; csq[j] += x * x; }
                     else {
-                        double* d = p.bn_sums + ((size_t)(m / rows_per_group) * N + n) * 2;
+                        double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * groups + m / rows_per_group) * N + n) * 2;
                         atomicAdd(d, (double)x);
                         atomicAdd(d + 1, (double)x * x);
                     }
@@ -213,7 +214,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
         }
         __syncthreads();
         if (tid < BN && n0 + tid < N) {
-            double* d = p.bn_sums + ((size_t)(m0 / rows_per_group) * N + n0 + tid) * 2;
+            double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * groups + m0 / rows_per_group) * N + n0 + tid) * 2;
             atomicAdd(d, (double)s_stat[0][tid]);
             atomicAdd(d + 1, (double)s_stat[1][tid]);
         }

@@ -1,0 +1,327 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, kind::tf32, fp32 accumulate in TMEM).
+//
+//   C[M = B*Ho*Wo, N = Cout] = A[M, K = kh*kw*Cin] (im2col gather of the NHWC input) x W[N, K]^T
+//
+// CTA = one 128 x BN output tile, 5 warps:
+//   warps 0-3  producers: gather 128 x 32-float A slices (any stride / zero or reflection padding) and BN x 32 W
+//              slices with 16-byte loads, write them into the 128B-swizzled K-major layout the UMMA descriptors
+//              expect, fence.proxy.async, arrive on the stage's "full" mbarrier; afterwards they are the epilogue
+//              (tcgen05.ld 32x32b -> bias / activation / residual addend / BatchNorm partial sums -> 16B stores)
+//   warp 4     allocates TMEM, one elected lane issues 4 x tcgen05.mma (M128 x BN x K8) per stage and
+//              tcgen05.commit's to the stage's "empty" mbarrier / the accumulator-ready mbarrier.
+// A software gather is used instead of TMA-im2col because the same loader folds in reflection padding and the
+// transposed-convolution view used for the data gradient; the tile still never touches registers twice.
+//
+// dgrad (stride 1) is the same kernel run on dout with flipped/transposed weights (weight_flip_kernel below);
+// for reflection-padded layers it returns the gradient of the padded tensor (pad' = 2), folded afterwards.
+//
+// Replaces cuDNN implicit-GEMM fwd/dgrad for every layer with Cin % 4 == 0.
+#include "nn_common.cuh"
+#include "tc_common.cuh"
+
+namespace scsfm {
+
+constexpr int TBM = 128;            // tile rows (UMMA M)
+constexpr int TBK = 32;             // floats per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 160;
+constexpr int A_STAGE_BYTES = TBM * 128;
+
+template <int BN>
+struct TcCfg {
+    static constexpr int STAGES = BN >= 128 ? 3 : 4;
+    static constexpr int B_STAGE_BYTES = BN * 128;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_ELU: return v > 0.f ? v : expm1f(v);
+        case ACT_DISP: return 10.0f * (1.0f / (1.0f + expf(-v))) + 0.01f;
+        default: return v;
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_fwd_tc_kernel(ScsfmConv p) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + STAGES;
+    uint64_t* bar_acc = bar_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.B * p.Ho * p.Wo, N = p.Cout, K = p.kh * p.kw * p.Cin;
+    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
+    const int KB = (K + TBK - 1) / TBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(bar_full + s, 128);
+            tc::mbar_init(bar_empty + s, 1);
+        }
+        tc::mbar_init(bar_acc, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers
+        const int c = tid & 7;               // 16-byte chunk column inside the 128-byte row
+        const int r0 = tid >> 3;             // rows r0 + 16*i
+        const int cs = c ^ (r0 & 7);         // 128B swizzle: chunk ^= row % 8 (rows r0+16i share row % 8)
+        int hi0[8], wi0[8];
+        const float* base[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + r0 + 16 * i;
+            if (m < M) {
+                const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
+                hi0[i] = ho * p.stride - p.pad;
+                wi0[i] = wo * p.stride - p.pad;
+                base[i] = p.in + (size_t)b * p.Hi * p.Wi * p.Cin;
+            } else {
+                hi0[i] = -(1 << 28);          // always out of range -> zero rows
+                wi0[i] = -(1 << 28);
+                base[i] = p.in;
+            }
+        }
+        int kc = 4 * c;
+        int tap = kc / p.Cin, ch = kc - tap * p.Cin;
+        int dy = tap / p.kw, dx = tap - dy * p.kw;
+        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            tc::mbar_wait(bar_empty + s, ph ^ 1);
+            float4 va[8], vb[BN / 16];
+            const bool kok = kc < K;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int hi = hi0[i] + dy, wi = wi0[i] + dx;
+                bool ok = kok;
+                if (reflect) {
+                    ok = ok && hi0[i] > -(1 << 27);
+                    hi = reflect_index(hi, p.Hi);
+                    wi = reflect_index(wi, p.Wi);
+                } else {
+                    ok = ok && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                }
+                va[i] = ok ? __ldg(reinterpret_cast<const float4*>(base[i] + ((size_t)hi * p.Wi + wi) * p.Cin + ch))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 16; ++j) {
+                const int n = n0 + r0 + 16 * j;
+                vb[j] = (kok && n < N) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * K + kc))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint8_t* a_st = sA + s * A_STAGE_BYTES + cs * 16;
+            uint8_t* b_st = sB + s * Cfg::B_STAGE_BYTES + cs * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = va[i];
+#pragma unroll
+            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = vb[j];
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_full + s);
+            // advance this thread's K index by one k-block
+            kc += TBK;
+            ch += TBK;
+            while (ch >= p.Cin) {
+                ch -= p.Cin;
+                if (++dx == p.kw) { dx = 0; ++dy; }
+            }
+        }
+
+        // ------------------------------------------------------------------ epilogue (same 4 warps)
+        tc::mbar_wait(bar_acc, 0);
+        tc::fence_after_thread_sync();
+        const int m = m0 + warp * 32 + lane;
+        const bool row_ok = m < M;
+        float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
+        constexpr int CW = BN < 32 ? BN : 32;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / CW; ++cc) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * CW);
+            if (CW == 32) tc::tmem_ld32(taddr, r);
+            else tc::tmem_ld16(taddr, r);
+            tc::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const int n = n0 + cc * CW + j;
+                float x = __uint_as_float(r[j]);
+                if (row_ok && n < N) {
+                    if (p.bias) x += __ldg(p.bias + n);
+                    if (p.addend) x += __ldg(p.addend + (size_t)m * N + n);
+                    x = tc_act(x, p.act);
+                } else {
+                    x = 0.f;
+                }
+                v[j] = x;
+            }
+            if (row_ok) {
+                float* o = p.out + (size_t)m * N + n0 + cc * CW;
+                if ((N & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4)
+                        if (n0 + cc * CW + j < N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j)
+                        if (n0 + cc * CW + j < N) o[j] = v[j];
+                }
+            }
+            if (p.bn_sums != nullptr) {
+                // column sums over the warp's 32 rows through a padded smem transpose, then fp64 atomics into one of
+                // SCSFM_BN_SLOTS replicas (spreads the per-address serialisation at L2)
+#pragma unroll
+                for (int j = 0; j < CW; ++j) stage[lane * 33 + j] = v[j];
+                __syncwarp();
+                if (lane < CW) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float t = stage[rr * 33 + lane];
+                        s1 += t;
+                        s2 += t * t;
+                    }
+                    const int n = n0 + cc * CW + lane;
+                    if (n < N) {
+                        const int rows_per_group = (p.B / (p.bn_groups > 0 ? p.bn_groups : 1)) * p.Ho * p.Wo;
+                        const int g = m0 / rows_per_group;        // host guarantees tiles do not straddle groups
+                        double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * (p.bn_groups > 0 ? p.bn_groups : 1) + g) * N + n) * 2;
+                        atomicAdd(d, (double)s1);
+                        atomicAdd(d + 1, (double)s2);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (warp 4)
+        constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 0, 0);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            tc::mbar_wait(bar_full + s, ph);
+            tc::fence_after_thread_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
+                const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < TBK / 8; ++j) {
+                    const uint64_t da = tc::make_smem_desc(a_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
+                    const uint64_t db = tc::make_smem_desc(b_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
+                    tc::mma_tf32(tmem_base, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+                }
+                tc::mma_commit(bar_empty + s);           // frees the stage once these MMAs have read it
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tc::mma_commit(bar_acc);          // accumulator complete
+        __syncwarp();
+    }
+
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// w [Co][T][Ci] -> wt [Ci][T][Co] with the taps reversed: the weights of the transposed (data-gradient) conv
+__global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int T, int Ci, float* __restrict__ wt) {
+    const long long total = (long long)Co * T * Ci;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int o = (int)(i % Co);
+        const long long t2 = i / Co;
+        const int tap = (int)(t2 % T), c = (int)(t2 / T);
+        wt[i] = __ldg(w + ((size_t)o * T + (T - 1 - tap)) * Ci + c);
+    }
+}
+
+template <int BN>
+static int launch_fwd_tc(const ScsfmConv& p, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int M = p.B * p.Ho * p.Wo;
+    dim3 grid((M + TBM - 1) / TBM, (p.Cout + BN - 1) / BN);
+    conv_fwd_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+}  // namespace scsfm
+
+using namespace scsfm;
+
+static int tc_dispatch(const ScsfmConv& p, cudaStream_t st) {
+    const int N = p.Cout;
+    if (N <= 16) return launch_fwd_tc<16>(p, st);
+    if (N <= 32 || N % 64 != 0) return launch_fwd_tc<32>(p, st);
+    if (N <= 64 || N % 128 != 0) return launch_fwd_tc<64>(p, st);
+    // prefer more CTAs when the M extent is small (deep layers at 8x26 / 16x52)
+    const int M = p.B * p.Ho * p.Wo;
+    if (((M + TBM - 1) / TBM) * (N / 128) < 148) return launch_fwd_tc<64>(p, st);
+    return launch_fwd_tc<128>(p, st);
+}
+
+static int check_tc(const ScsfmConv* p, const char* who) {
+    SCSFM_CHECK_ARG(p != nullptr && p->in && p->w && p->out, "%s: null tensor", who);
+    SCSFM_CHECK_ARG(p->B > 0 && p->Hi > 0 && p->Wi > 0 && p->Cin > 0 && p->Cout > 0 && p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0,
+                    "%s: bad geometry", who);
+    SCSFM_CHECK_ARG((p->Cin & 3) == 0, "%s: the tensor-core kernel needs Cin %% 4 == 0 (got %d); use the CUDA-core kernel", who, p->Cin);
+    SCSFM_CHECK_ARG(p->Ho == (p->Hi + 2 * p->pad - p->kh) / p->stride + 1 && p->Wo == (p->Wi + 2 * p->pad - p->kw) / p->stride + 1,
+                    "%s: output size does not match geometry", who);
+    SCSFM_CHECK_ARG(p->pad_mode != PADMODE_REFLECT || p->pad == 1, "%s: reflect pad must be 1", who);
+    if (p->bn_sums) {
+        const int g = p->bn_groups > 0 ? p->bn_groups : 1;
+        SCSFM_CHECK_ARG(p->B % g == 0 && (g == 1 || ((p->B / g) * p->Ho * p->Wo) % TBM == 0), "%s: BatchNorm groups must align with 128-row tiles", who);
+    }
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream) {
+    if (int rc = check_tc(p, "conv2d_fwd_tc")) return rc;
+    return tc_dispatch(*p, (cudaStream_t)stream);
+}
+
+extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream) {
+    SCSFM_CHECK_ARG(w && wt && Cout > 0 && kh > 0 && kw > 0 && Cin > 0, "weight_flip: bad arguments");
+    const long long total = (long long)Cout * kh * kw * Cin;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh * kw, Cin, wt);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+// stride-1 data gradient = forward kernel on dout with the flipped weights `wt` ([Cin][kh][kw][Cout], from
+// scsfm_weight_flip) passed in p->w; p->din [B,Hi,Wi,Cin] (+ p->addend).
+extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
+    SCSFM_CHECK_ARG(p != nullptr && p->dout && p->w && p->din, "conv2d_dgrad_tc: null tensor");
+    SCSFM_CHECK_ARG(p->stride == 1, "conv2d_dgrad_tc: stride must be 1 (strided layers use the CUDA-core kernel)");
+    ScsfmConv q = *p;
+    q.in = p->dout; q.out = p->din; q.bias = nullptr; q.bn_sums = nullptr; q.act = SCSFM_ACT_NONE;
+    q.Hi = p->Ho; q.Wi = p->Wo; q.Cin = p->Cout;
+    q.Ho = p->Hi; q.Wo = p->Wi; q.Cout = p->Cin;
+    q.pad = p->kh - 1 - p->pad; q.pad_mode = SCSFM_PADMODE_ZERO;
+    SCSFM_CHECK_ARG(p->kh == p->kw && q.pad >= 0, "conv2d_dgrad_tc: square kernels only");
+    if (int rc = check_tc(&q, "conv2d_dgrad_tc")) return rc;
+    return tc_dispatch(q, (cudaStream_t)stream);
+}

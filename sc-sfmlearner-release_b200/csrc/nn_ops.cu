@@ -53,7 +53,11 @@ __global__ void bn_prepare_kernel(const double* __restrict__ sums, int G, int C,
     if (training) {
         float rm = rmean[c], rv = rvar[c];
         for (int grp = 0; grp < G; ++grp) {
-            const double s = sums[((size_t)grp * C + c) * 2], q = sums[((size_t)grp * C + c) * 2 + 1];
+            double s = 0.0, q = 0.0;
+            for (int slot = 0; slot < SCSFM_BN_SLOTS; ++slot) {
+                s += sums[(((size_t)slot * G + grp) * C + c) * 2];
+                q += sums[(((size_t)slot * G + grp) * C + c) * 2 + 1];
+            }
             const double mean = s / count;
             double var = q / count - mean * mean;
             if (var < 0) var = 0;

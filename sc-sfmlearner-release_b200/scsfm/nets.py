@@ -289,7 +289,7 @@ def _bn_fwd(y, sums, bn, training, relu, residual=None):
 
 def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None):
     C = conv.weight.shape[0]
-    sums = torch.zeros(C * 2, device=x.device, dtype=torch.float64) if training else None
+    sums = torch.zeros(O.BN_SLOTS * C * 2, device=x.device, dtype=torch.float64) if training else None
     y = O.conv_fwd(x, conv.w_khwc(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, 1)
     z, saved = _bn_fwd(y, sums, bn, training, relu, residual)
     return y, z, saved
@@ -318,7 +318,7 @@ def block_forward(blk, x, training):
     if blk.downsample is not None:
         r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False)
     C = last_conv.weight.shape[0]
-    sums = torch.zeros(C * 2, device=x.device, dtype=torch.float64) if training else None
+    sums = torch.zeros(O.BN_SLOTS * C * 2, device=x.device, dtype=torch.float64) if training else None
     y = O.conv_fwd(last_in, last_conv.w_khwc(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, 1)
     out, saved = _bn_fwd(y, sums, last_bn, training, True, sc)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
@@ -560,6 +560,7 @@ class ArenaAdam:
             m, v, _ = self.state[key]
             O.adam_step(n._flat, n._flat_grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                         self.step_count)
+        O.invalidate_weight_cache()        # flipped dgrad weights are stale after the update
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": [self.state[id(n)][0] for n in self.nets if id(n) in self.state],

@@ -11,6 +11,7 @@ from . import lib as L
 
 PAD_ZERO, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_DISP = 0, 1, 2, 3
+BN_SLOTS = 16      # SCSFM_BN_SLOTS: replicas of the fused BatchNorm sums
 
 # "fp32": exact CUDA-core kernels everywhere (parity mode).  "tf32": tcgen05 tensor-core kernels on the
 # layers they support (same arithmetic class as the reference's cuDNN TF32 default on GPU).
@@ -37,6 +38,8 @@ def _lib():
                      "scsfm_conv2d_fwd_tc", "scsfm_conv2d_dgrad_tc", "scsfm_conv2d_wgrad_tc"):
             if hasattr(lib, name):
                 getattr(lib, name).argtypes = [CP, P]
+        if hasattr(lib, "scsfm_weight_flip"):
+            lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
@@ -67,7 +70,32 @@ def _use_tc(kind, Cin, Cout, kh, stride):
 
 def tc_supported(kind, Cin, Cout, kh, stride):
     """Shapes the tcgen05 kernels take; everything else runs the CUDA-core kernel."""
+    if kind == "fwd":
+        return Cin % 4 == 0 and Cout >= 16
+    if kind == "dgrad":                      # forward kernel on dout: its "Cin" is Cout, its "Cout" is Cin
+        return stride == 1 and Cout % 4 == 0 and Cin >= 16
     return False
+
+
+_flip_cache = {}
+
+
+def flipped_weights(w):
+    """[Cout,kh,kw,Cin] -> [Cin,kh,kw,Cout] with reversed taps (weights of the transposed conv), cached per
+    weight tensor until `invalidate_weight_cache()` is called (after every optimizer step)."""
+    key = (w.data_ptr(), tuple(w.shape))
+    wt = _flip_cache.get(key)
+    if wt is None:
+        Cout, kh, kw, Cin = w.shape
+        wt = empty((Cin, kh, kw, Cout), w)
+        L.launch(_lib().scsfm_weight_flip, "scsfm_weight_flip", "weight_flip", 1, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw, Cin,
+                 L.ptr(wt), L.stream())
+        _flip_cache[key] = wt
+    return wt
+
+
+def invalidate_weight_cache():
+    _flip_cache.clear()
 
 
 def conv_desc(x_shape, w, stride, pad, pad_mode, act):
@@ -109,6 +137,8 @@ def conv_dgrad(dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=Fals
     din = empty((B, Hi, Wi, Cin), dout)
     d.dout, d.din, d.addend = dout.data_ptr(), din.data_ptr(), addend.data_ptr() if addend is not None else None
     tc = _use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
+    if tc:
+        d.w = flipped_weights(w).data_ptr()
     fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
     L.launch(fn, "scsfm_conv2d_dgrad", "conv_dgrad_tc" if tc else "conv_dgrad_simt", 1, _flops(d), ctypes.byref(d), L.stream())
     return din
