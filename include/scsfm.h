@@ -171,6 +171,7 @@ int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
  * scsfm_weight_flip (the data gradient is the forward kernel run on dout). */
 int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream);
+int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream);
 int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
 
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
@@ -215,9 +216,10 @@ int scsfm_act_bwd(float* d, const float* out, long long n, int act, void* stream
 int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, float scale, float* out, void* stream);
 int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream);
 
-/* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena. step >= 1. */
+/* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena.  The 1-based step count is
+ * `step`, or *step_dev (device int) when step_dev != NULL so that a captured CUDA graph stays valid. */
 int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+                    float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(CT)
 conv_fwd_simt_kernel(ScsfmConv p) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
-    __shared__ float s_stat[2][BN];
+    __shared__ double s_stat[2][BN];
     const int tid = threadIdx.x, tx = tid % (BN / 4), ty = tid / (BN / 4);
     const int M = p.B * p.Ho * p.Wo, N = p.Cout, K = p.kh * p.kw * p.Cin;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -169,7 +169,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
     }
 
     // epilogue: bias, activation, store, optional BatchNorm partial sums (per group of samples)
-    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
+    double csum[4] = {0.0, 0.0, 0.0, 0.0}, csq[4] = {0.0, 0.0, 0.0, 0.0};   // fp64: see conv_tc.cu (variance cancellation)
     const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
     const int rows_per_group = (p.B / groups) * p.Ho * p.Wo;
     const bool want_stats = p.bn_sums != nullptr;
@@ -187,7 +187,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
                 if (p.bias) x += __ldg(p.bias + n);
                 x = apply_act(x, p.act);
                 if (want_stats) {
-                    if (uniform_group) { csum[j] += x; csq[j] += x * x; }
+                    if (uniform_group) { csum[j] += (double)x; csq[j] += (double)x * (double)x; }
                     else {
                         double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * groups + m / rows_per_group) * N + n) * 2;
                         atomicAdd(d, (double)x);
@@ -205,7 +205,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
                 if (n0 + tx * 4 + j < N) o[j] = v[j];
     }
     if (want_stats && uniform_group) {
-        if (tid < BN) { s_stat[0][tid] = 0.f; s_stat[1][tid] = 0.f; }
+        if (tid < BN) { s_stat[0][tid] = 0.0; s_stat[1][tid] = 0.0; }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -215,8 +215,8 @@ conv_fwd_simt_kernel(ScsfmConv p) {
         __syncthreads();
         if (tid < BN && n0 + tid < N) {
             double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * groups + m0 / rows_per_group) * N + n0 + tid) * 2;
-            atomicAdd(d, (double)s_stat[0][tid]);
-            atomicAdd(d + 1, (double)s_stat[1][tid]);
+            atomicAdd(d, s_stat[0][tid]);
+            atomicAdd(d + 1, s_stat[1][tid]);
         }
     }
 }
@@ -440,6 +440,16 @@ bias_grad_kernel(const float* __restrict__ dout, int rows, int C, float* __restr
     }
 }
 
+// host-side launcher shared with the tensor-core weight gradient (conv_tc.cu)
+int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st) {
+    int ctas = (rows + 2047) / 2048;
+    if (ctas > 592) ctas = 592;
+    const int rpc = (rows + ctas - 1) / ctas;
+    bias_grad_kernel<<<dim3((rows + rpc - 1) / rpc, (C + 63) / 64), CT, 0, st>>>(dout, rows, C, dbias, rpc);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
 }  // namespace scsfm
 
 using namespace scsfm;
@@ -499,13 +509,6 @@ extern "C" int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream) {
     else if (M <= 32) { plan(32, 128, grid, kps); conv_wgrad_simt_kernel<32, 128><<<grid, CT, 0, st>>>(*p, kps); }
     else { plan(64, 64, grid, kps); conv_wgrad_simt_kernel<64, 64><<<grid, CT, 0, st>>>(*p, kps); }
     SCSFM_CHECK_LAUNCH();
-    if (p->dbias) {
-        const int rows = Kall;
-        int ctas = (rows + 2047) / 2048;
-        if (ctas > 592) ctas = 592;
-        const int rpc = (rows + ctas - 1) / ctas;
-        bias_grad_kernel<<<dim3((rows + rpc - 1) / rpc, (M + 63) / 64), CT, 0, st>>>(p->dout, rows, M, p->dbias, rpc);
-        SCSFM_CHECK_LAUNCH();
-    }
+    if (p->dbias) return launch_bias_grad(p->dout, Kall, M, p->dbias, st);
     return SCSFM_OK;
 }

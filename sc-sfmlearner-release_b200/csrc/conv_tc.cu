@@ -34,6 +34,15 @@ struct TcCfg {
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 };
 
+// fp32 -> tf32 with round-to-nearest (the tensor core would otherwise TRUNCATE the low 13 mantissa bits, a
+// systematic -7e-4 relative bias on every dot product; measured in tools/debug_tc.py)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+
 __device__ __forceinline__ float tc_act(float v, int act) {
     switch (act) {
         case ACT_RELU: return fmaxf(v, 0.f);
@@ -130,9 +139,9 @@ conv_fwd_tc_kernel(ScsfmConv p) {
             uint8_t* a_st = sA + s * A_STAGE_BYTES + cs * 16;
             uint8_t* b_st = sB + s * Cfg::B_STAGE_BYTES + cs * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = va[i];
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = tf32_rn4(va[i]);
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = vb[j];
+            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = tf32_rn4(vb[j]);
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_full + s);
             // advance this thread's K index by one k-block
@@ -191,20 +200,32 @@ conv_fwd_tc_kernel(ScsfmConv p) {
                 for (int j = 0; j < CW; ++j) stage[lane * 33 + j] = v[j];
                 __syncwarp();
                 if (lane < CW) {
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const float t = stage[rr * 33 + lane];
+                    // a tile may straddle BatchNorm groups (network calls batched into one launch): walk the warp's
+                    // 32 rows and flush the column sums whenever the group changes
+                    const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
+                    const int rows_per_group = (p.B / groups) * p.Ho * p.Wo;
+                    const int row_base = m0 + warp * 32;
+                    const int n = n0 + cc * CW + lane;
+                    int g_cur = row_base / rows_per_group;
+                    int next_edge = (g_cur + 1) * rows_per_group - row_base;      // first row index of the next group
+                    // fp64 accumulation: var = E[x^2] - mean^2 cancels catastrophically when |mean| >> std, so the
+                    // partial sums must not carry fp32 rounding (B200 issues DFMA at half the FFMA rate: negligible here)
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int rr = 0; rr <= 32; ++rr) {
+                        if (rr == 32 || rr == next_edge) {
+                            if (n < N && g_cur < groups && (s1 != 0.0 || s2 != 0.0)) {
+                                double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * groups + g_cur) * N + n) * 2;
+                                atomicAdd(d, s1);
+                                atomicAdd(d + 1, s2);
+                            }
+                            if (rr == 32) break;
+                            s1 = 0.0; s2 = 0.0;
+                            ++g_cur;
+                            next_edge += rows_per_group;
+                        }
+                        const double t = (double)stage[rr * 33 + lane];
                         s1 += t;
                         s2 += t * t;
-                    }
-                    const int n = n0 + cc * CW + lane;
-                    if (n < N) {
-                        const int rows_per_group = (p.B / (p.bn_groups > 0 ? p.bn_groups : 1)) * p.Ho * p.Wo;
-                        const int g = m0 / rows_per_group;        // host guarantees tiles do not straddle groups
-                        double* d = p.bn_sums + (((size_t)(blockIdx.x % SCSFM_BN_SLOTS) * (p.bn_groups > 0 ? p.bn_groups : 1) + g) * N + n) * 2;
-                        atomicAdd(d, (double)s1);
-                        atomicAdd(d + 1, (double)s2);
                     }
                 }
                 __syncwarp();
@@ -251,6 +272,209 @@ __global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int T, i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient on the tensor cores:  dW^T[(tap,c), o] += sum_pix  in[pix (+) tap, c] * dout[pix, o]
+//   GEMM  M = kh*kw*Cin (gathered input, "MN-major": channels contiguous),  N = Cout (dout, "MN-major"),
+//   K = B*Ho*Wo pixels, split over gridDim.z; partial tiles are added into dw with fp32 atomics.
+// Both operands are MN-major (channels contiguous).  For 32-bit MN-major operands the only shared-memory layout the
+// UMMA unit accepts is SWIZZLE_128B_BASE32B (layout type 1): atom = 4 pixels (K) x 32 channels (128-byte rows),
+// 32-byte chunks XOR-swizzled with (pixel % 4); atoms along M/N at LBO = 512 B, 4-pixel groups at SBO.  One
+// tcgen05.mma (K = 8 for tf32) therefore consumes two pixel groups.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct WgCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int A_BYTES = 32 * TBM * 4;        // 32 pixels x 128 (tap,c)
+    static constexpr int B_BYTES = 32 * BN * 4;         // 32 pixels x BN output channels
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
+    using Cfg = WgCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+    uint64_t* bar_empty = bar_full + STAGES;
+    uint64_t* bar_acc = bar_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Mtot = p.kh * p.kw * p.Cin, N = p.Cout, npix = p.B * p.Ho * p.Wo;
+    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
+    const int pix_begin = blockIdx.z * pix_per_split, pix_end = min(npix, pix_begin + pix_per_split);
+    const int KB = (pix_end - pix_begin + 31) / 32;
+    if (KB <= 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(bar_full + s, 128);
+            tc::mbar_init(bar_empty + s, 1);
+        }
+        tc::mbar_init(bar_acc, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers
+        // A: chunk c4 = tid % 32 (4 consecutive (tap,c) entries, fixed for the whole kernel), pixel rows tid/32 + 4*i
+        const int c4 = tid & 31, kr0 = tid >> 5;
+        const int mm = m0 + 4 * c4;
+        const bool a_ok = mm < Mtot;
+        int a_dy = 0, a_dx = 0, a_ch = 0;
+        if (a_ok) {
+            const int tap = mm / p.Cin;
+            a_ch = mm - tap * p.Cin;
+            a_dy = tap / p.kw;
+            a_dx = tap - a_dy * p.kw;
+        }
+        const int a_off = (c4 >> 3) * 512;                  // atom along M
+        const int a_chunk = c4 & 7;
+        // B: BN/4 chunks per pixel row
+        constexpr int BCH = BN / 4;                          // chunks per row: 8, 16 or 32
+        constexpr int B_IT = (32 * BCH) / 128;               // per-thread chunk loads: 2, 4, 8
+        const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
+        const int nn = n0 + 4 * b_c4;
+        const bool b_ok = nn < N;
+        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
+        int pb, pho, pwo;
+        {
+            const int px = pix_begin + kr0;
+            pb = px / (p.Ho * p.Wo);
+            const int rem = px - pb * p.Ho * p.Wo;
+            pho = rem / p.Wo;
+            pwo = rem - pho * p.Wo;
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            tc::mbar_wait(bar_empty + s, ph ^ 1);
+            const int pix0 = pix_begin + kb * 32;
+            float4 va[8], vb[B_IT];
+            {
+                int b = pb, ho = pho, wo = pwo;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int px = pix0 + kr0 + 4 * i;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a_ok && px < pix_end) {
+                        int hi = ho * p.stride + a_dy - p.pad, wi = wo * p.stride + a_dx - p.pad;
+                        bool ok = true;
+                        if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
+                        else ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                        if (ok) v = __ldg(reinterpret_cast<const float4*>(p.in + (((size_t)b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch));
+                    }
+                    va[i] = v;
+                    wo += 4;
+                    while (wo >= p.Wo) { wo -= p.Wo; if (++ho == p.Ho) { ho = 0; ++b; } }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int px = pix0 + b_kr0 + (128 / BCH) * i;
+                vb[i] = (b_ok && px < pix_end) ? __ldg(reinterpret_cast<const float4*>(p.dout + (size_t)px * N + nn))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint8_t* a_st = sA + s * Cfg::A_BYTES + a_off;
+            uint8_t* b_st = sB + s * Cfg::B_BYTES + (b_c4 >> 3) * 512;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kr0 + 4 * i;                  // pixel row inside the block: group k/4, row k%4
+                *reinterpret_cast<float4*>(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16)) = tf32_rn4(va[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int k = b_kr0 + (128 / BCH) * i;
+                *reinterpret_cast<float4*>(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16)) = tf32_rn4(vb[i]);
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_full + s);
+            pwo += 32;
+            while (pwo >= p.Wo) { pwo -= p.Wo; if (++pho == p.Ho) { pho = 0; ++pb; } }
+        }
+
+        // ------------------------------------------------------------------ epilogue: dw[o][mm] += D[mm][o]
+        tc::mbar_wait(bar_acc, 0);
+        tc::fence_after_thread_sync();
+        const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), r);
+            tc::tmem_ld_wait();
+            if (row < Mtot) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int o = n0 + cc * 32 + j;
+                    if (o < N) red_add(p.dw + (size_t)o * Mtot + row, __uint_as_float(r[j]));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (warp 4)
+        constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 1, 1);       // both operands MN-major
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            tc::mbar_wait(bar_full + s, ph);
+            tc::fence_after_thread_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = tc::smem_u32(sA + s * Cfg::A_BYTES);
+                const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {               // 4 pixel groups of 8 (UMMA K = 8 for tf32)
+                    // LBO = 512 B between 32-channel atoms, SBO = distance between 4-pixel groups; 2 groups per MMA
+                    const uint64_t da = tc::make_smem_desc(a_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
+                    const uint64_t db = tc::make_smem_desc(b_addr + j * (2 * (BN / 32) * 512), 512, (BN / 32) * 512, tc::LAYOUT_SW128_BASE32B);
+                    tc::mma_tf32(tmem_base, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+                }
+                tc::mma_commit(bar_empty + s);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tc::mma_commit(bar_acc);
+        __syncwarp();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
+
+template <int BN>
+static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
+    using Cfg = WgCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * p.Ho * p.Wo;
+    const int mt = (Mtot + TBM - 1) / TBM, nt = (p.Cout + BN - 1) / BN;
+    int splits = (148 * 2 + mt * nt - 1) / (mt * nt);
+    const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
+    dim3 grid(mt, nt, (npix + pps - 1) / pps);
+    conv_wgrad_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p, pps);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
 template <int BN>
 static int launch_fwd_tc(const ScsfmConv& p, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
@@ -291,7 +515,7 @@ static int check_tc(const ScsfmConv* p, const char* who) {
     SCSFM_CHECK_ARG(p->pad_mode != PADMODE_REFLECT || p->pad == 1, "%s: reflect pad must be 1", who);
     if (p->bn_sums) {
         const int g = p->bn_groups > 0 ? p->bn_groups : 1;
-        SCSFM_CHECK_ARG(p->B % g == 0 && (g == 1 || ((p->B / g) * p->Ho * p->Wo) % TBM == 0), "%s: BatchNorm groups must align with 128-row tiles", who);
+        SCSFM_CHECK_ARG(p->B % g == 0, "%s: batch not divisible by the number of BatchNorm groups", who);
     }
     return SCSFM_OK;
 }
@@ -324,4 +548,22 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG(p->kh == p->kw && q.pad >= 0, "conv2d_dgrad_tc: square kernels only");
     if (int rc = check_tc(&q, "conv2d_dgrad_tc")) return rc;
     return tc_dispatch(q, (cudaStream_t)stream);
+}
+
+// dw [Cout,kh,kw,Cin] += dout^T x gather(in); dbias += column sums of dout.  Needs Cin % 4 == 0 and Cout % 4 == 0.
+extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
+    SCSFM_CHECK_ARG(p != nullptr && p->in && p->dout && p->dw, "conv2d_wgrad_tc: null tensor");
+    SCSFM_CHECK_ARG(p->B > 0 && p->Hi > 0 && p->Wi > 0 && p->Cin > 0 && p->Cout > 0 && p->kh > 0 && p->kw > 0 && p->stride > 0 && p->pad >= 0,
+                    "conv2d_wgrad_tc: bad geometry");
+    SCSFM_CHECK_ARG((p->Cin & 3) == 0 && (p->Cout & 3) == 0, "conv2d_wgrad_tc: needs Cin %% 4 == 0 and Cout %% 4 == 0");
+    SCSFM_CHECK_ARG(p->pad_mode != PADMODE_REFLECT || p->pad == 1, "conv2d_wgrad_tc: reflect pad must be 1");
+    SCSFM_CHECK_ARG((long long)p->B * p->Ho * p->Wo < (1LL << 31), "conv2d_wgrad_tc: too many pixels");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
+    else if (p->Cout <= 64) rc = launch_wgrad_tc<64>(*p, st);
+    else rc = launch_wgrad_tc<128>(*p, st);
+    if (rc) return rc;
+    if (p->dbias) return launch_bias_grad(p->dout, p->B * p->Ho * p->Wo, p->Cout, p->dbias, st);
+    return SCSFM_OK;
 }

@@ -110,33 +110,65 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
 }
 
 // pass 1: work[g][c] = { sum dz', sum dz' * xhat }  (dz' = dz gated by relu)
+// One CTA = a chunk of rows x a slab of up to 1024 channels; every thread owns 4 consecutive channels
+// (float4 loads, a row of the slab is one contiguous segment) and strides over the chunk's rows.
 __global__ void __launch_bounds__(NT)
 bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
                      const float* __restrict__ saved, long long rows_per_group, int C, int relu, int rows_per_cta,
                      double* __restrict__ work) {
-    // blockIdx.y = group, blockIdx.z = 64-channel slab, blockIdx.x = row chunk
-    const int g = blockIdx.y, c = blockIdx.z * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
+    const int g = blockIdx.y;
+    const int slab4 = min(C >> 2, NT);                    // float4 columns handled by this CTA
+    const int col4 = blockIdx.z * slab4 + (threadIdx.x % slab4);
+    const int row_lanes = NT / slab4, rl = threadIdx.x / slab4;
+    const int c = col4 * 4;
     const long long r0 = (long long)g * rows_per_group + (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min((long long)(g + 1) * rows_per_group, r0 + rows_per_cta);
-    float s0 = 0.f, s1 = 0.f;
-    if (c < C) {
-        const float mean = saved[((size_t)g * C + c) * 4 + 2], invstd = saved[((size_t)g * C + c) * 4 + 3];
-        for (long long r = r0 + rl; r < r1; r += NT / 64) {
-            float d = __ldg(dz + r * C + c);
-            if (relu && !(__ldg(z + r * C + c) > 0.f)) d = 0.f;
-            s0 += d;
-            s1 += d * ((__ldg(y + r * C + c) - mean) * invstd);
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool active = c < C && rl < row_lanes;
+    if (active) {
+        float mean[4], invstd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mean[j] = saved[((size_t)g * C + c + j) * 4 + 2];
+            invstd[j] = saved[((size_t)g * C + c + j) * 4 + 3];
+        }
+        for (long long r = r0 + rl; r < r1; r += row_lanes) {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dz + r * C + c));
+            const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
+            float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+            if (relu) {
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+                if (!(z4.x > 0.f)) d[0] = 0.f;
+                if (!(z4.y > 0.f)) d[1] = 0.f;
+                if (!(z4.z > 0.f)) d[2] = 0.f;
+                if (!(z4.w > 0.f)) d[3] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s0[j] += d[j];
+                s1[j] += d[j] * ((yy[j] - mean[j]) * invstd[j]);
+            }
         }
     }
-    __shared__ float sh[2][NT];
-    sh[0][threadIdx.x] = s0;
-    sh[1][threadIdx.x] = s1;
+    __shared__ float sh[8][NT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sh[j][threadIdx.x] = s0[j];
+        sh[4 + j][threadIdx.x] = s1[j];
+    }
     __syncthreads();
-    if (threadIdx.x < 64 && c < C) {
-        const float a = sh[0][threadIdx.x] + sh[0][threadIdx.x + 64] + sh[0][threadIdx.x + 128] + sh[0][threadIdx.x + 192];
-        const float b = sh[1][threadIdx.x] + sh[1][threadIdx.x + 64] + sh[1][threadIdx.x + 128] + sh[1][threadIdx.x + 192];
-        atomicAdd(work + ((size_t)g * C + c) * 2, (double)a);
-        atomicAdd(work + ((size_t)g * C + c) * 2 + 1, (double)b);
+    if (threadIdx.x < slab4 && c < C) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < row_lanes; ++l) {
+                a += sh[j][l * slab4 + threadIdx.x];
+                b += sh[4 + j][l * slab4 + threadIdx.x];
+            }
+            atomicAdd(work + ((size_t)g * C + c + j) * 2, (double)a);
+            atomicAdd(work + ((size_t)g * C + c + j) * 2 + 1, (double)b);
+        }
     }
 }
 
@@ -397,9 +429,14 @@ __global__ void spatial_mean_bwd_kernel(const float* __restrict__ dout, int B, i
 
 // ----- Adam ---------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+                            long long n, float lr, float b1, float b2, float eps, float wd, int step_host,
+                            const int* __restrict__ step_dev) {
     // torch.optim.Adam (non-amsgrad): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
-    // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+    // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  The step count may live on the device so that a captured
+    // CUDA graph of the training step stays valid across replays.
+    const int step = step_dev ? *step_dev : step_host;
+    const float bc1 = 1.0f - powf(b1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(b2, (float)step));
     const float step_size = lr / bc1;
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
         float gr = g[i];
@@ -461,10 +498,16 @@ extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y
     SCSFM_CHECK_ARG(!relu || z, "bn_backward: relu gate needs z");
     const long long rpg = rows / groups;
     SCSFM_CHECK_CUDA(cudaMemsetAsync(work, 0, (size_t)groups * C * 2 * sizeof(double), ST));
-    int chunks = (int)((rpg + 1023) / 1024);
-    if (chunks > 296) chunks = 296;
-    const int rpc = (int)((rpg + chunks - 1) / chunks);
-    bn_bwd_reduce_kernel<<<dim3((unsigned)((rpg + rpc - 1) / rpc), groups, (C + 63) / 64), NT, 0, ST>>>(dz, z, y, saved, rpg, C, relu, rpc, work);
+    const int slab4 = (C / 4) < NT ? (C / 4) : NT;
+    const int slabs = (C / 4 + slab4 - 1) / slab4;
+    const int row_lanes = NT / slab4;
+    // enough CTAs to fill the machine (4 per SM), at least 8 rows per row-lane per CTA
+    long long want = (148LL * 4 + (long long)groups * slabs - 1) / ((long long)groups * slabs);
+    long long max_chunks = (rpg + 8LL * row_lanes - 1) / (8LL * row_lanes);
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    const int rpc = (int)((rpg + want - 1) / want);
+    bn_bwd_reduce_kernel<<<dim3((unsigned)((rpg + rpc - 1) / rpc), groups, slabs), NT, 0, ST>>>(dz, z, y, saved, rpg, C, relu, rpc, work);
     SCSFM_CHECK_LAUNCH();
     bn_bwd_apply_kernel<<<grid_for(rows * (C / 4)), NT, 0, ST>>>(dz, z, y, saved, work, dy, dres, rows, C, rpg, relu);
     SCSFM_CHECK_LAUNCH();
@@ -542,11 +585,10 @@ extern "C" int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, f
 }
 
 extern "C" int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
-    SCSFM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
-    const float bc1 = 1.0f - powf(beta1, (float)step);
-    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+                               float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                               void* stream) {
+    SCSFM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
+    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

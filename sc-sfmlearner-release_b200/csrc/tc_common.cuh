@@ -99,6 +99,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 constexpr uint32_t LAYOUT_SW128 = 2;
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;   // 128-byte rows, 32-byte swizzle granularity: MN-major 32-bit operands
 
 // Instruction descriptor (32 bit) for kind::tf32 with fp32 accumulation:
 //   [4,6) D format (1 = F32) | [7,10) A format (2 = TF32) | [10,13) B format (2 = TF32) | [15] A major (0 = K) |

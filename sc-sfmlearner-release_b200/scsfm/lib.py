@@ -94,6 +94,9 @@ STATS = {"launches": 0}
 PROF = {"enabled": False, "only": None, "events": []}
 
 
+TAG = {"next": None}      # optional shape label attached to the next profiled launch (tools/profile_layers.py)
+
+
 def launch(fn, what, family, n_kernels, work, *args):
     """Call a C-ABI entry point; count its kernel launches; optionally bracket it with CUDA events on the
     launching stream.  `work` = algorithmic FLOPs (convs) or bytes (HBM-bound ops) of the call."""
@@ -103,7 +106,8 @@ def launch(fn, what, family, n_kernels, work, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROF["events"].append((family, work, e0, e1))
+        PROF["events"].append((family, work, e0, e1, TAG["next"]))
+        TAG["next"] = None
     else:
         rc = fn(*args)
     check(rc, what)

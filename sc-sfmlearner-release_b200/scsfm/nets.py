@@ -258,8 +258,8 @@ class ArenaNet(nn.Module):
 
 class _NetCall(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net, hook, *inputs):
-        rec, outs = net._forward_impl(*inputs)
+    def forward(ctx, net, hook, groups, *inputs):
+        rec, outs = net._forward_impl(groups, *inputs)
         ctx.net, ctx.rec = net, rec
         ctx.set_materialize_grads(False)     # unused outputs (scales 1-3 with --num-scales 1) arrive as None
         return tuple(outs)
@@ -273,54 +273,56 @@ class _NetCall(torch.autograd.Function):
         net._pending -= 1
         if net._pending == 0 and net.grads_ready_callback is not None:
             net.grads_ready_callback(net)
-        return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+        return (None, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 # ------------------------------------------------------------------------------------------------
 # encoder execution
 # ------------------------------------------------------------------------------------------------
-def _bn_fwd(y, sums, bn, training, relu, residual=None):
-    count = y.numel() // y.shape[-1]
-    saved = O.bn_prepare(sums, 1, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, training)
+def _bn_fwd(y, sums, bn, training, relu, residual, groups):
+    """BatchNorm over `groups` independent sample groups (one per batched network call: statistics, and the
+    running-stat updates, stay per call exactly as in train.py:427-442)."""
+    count = y.numel() // y.shape[-1] // groups
+    saved = O.bn_prepare(sums, groups, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, training)
     if training:
-        bn.num_batches_tracked += 1
-    return O.bn_apply(y, saved, residual, relu), saved
+        bn.num_batches_tracked += groups
+    return O.bn_apply(y, saved, residual, relu, groups), saved
 
 
-def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None):
+def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
     C = conv.weight.shape[0]
-    sums = torch.zeros(O.BN_SLOTS * C * 2, device=x.device, dtype=torch.float64) if training else None
-    y = O.conv_fwd(x, conv.w_khwc(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, 1)
-    z, saved = _bn_fwd(y, sums, bn, training, relu, residual)
+    sums = torch.zeros(O.BN_SLOTS * groups * C * 2, device=x.device, dtype=torch.float64) if training else None
+    y = O.conv_fwd(x, conv.w_khwc(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups)
+    z, saved = _bn_fwd(y, sums, bn, training, relu, residual, groups)
     return y, z, saved
 
 
-def _conv_bn_bwd(dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None):
+def _conv_bn_bwd(dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None, groups=1):
     """Backward through relu?(bn(conv(x)) [+res]).  Returns (dx or None, dres or None)."""
-    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, relu, want_dres)
+    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, relu, want_dres, groups)
     O.conv_wgrad(x, dy, ArenaNet.g(conv.weight), None, stride, pad, O.PAD_ZERO)
     dx = O.conv_dgrad(dy, conv.w_khwc(), x.shape, stride, pad, addend) if need_dx else None
     return dx, dres
 
 
-def block_forward(blk, x, training):
-    r = {"x": x}
+def block_forward(blk, x, training, G=1):
+    r = {"x": x, "G": G}
     if blk.bottleneck:
-        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, 1, 0, training, True)
-        r["y2"], r["h2"], r["s2"] = _conv_bn(r["h1"], blk.conv2, blk.bn2, blk.stride, 1, training, True)
+        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, 1, 0, training, True, None, G)
+        r["y2"], r["h2"], r["s2"] = _conv_bn(r["h1"], blk.conv2, blk.bn2, blk.stride, 1, training, True, None, G)
         last_in, last_conv, last_bn, key = r["h2"], blk.conv3, blk.bn3, "3"
         ls, lp = 1, 0
     else:
-        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, blk.stride, 1, training, True)
+        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, blk.stride, 1, training, True, None, G)
         last_in, last_conv, last_bn, key = r["h1"], blk.conv2, blk.bn2, "2"
         ls, lp = 1, 1
     sc = x
     if blk.downsample is not None:
-        r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False)
+        r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
     C = last_conv.weight.shape[0]
-    sums = torch.zeros(O.BN_SLOTS * C * 2, device=x.device, dtype=torch.float64) if training else None
-    y = O.conv_fwd(last_in, last_conv.w_khwc(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, 1)
-    out, saved = _bn_fwd(y, sums, last_bn, training, True, sc)
+    sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=x.device, dtype=torch.float64) if training else None
+    y = O.conv_fwd(last_in, last_conv.w_khwc(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G)
+    out, saved = _bn_fwd(y, sums, last_bn, training, True, sc, G)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
     return r, out
 
@@ -329,36 +331,36 @@ def block_backward(blk, r, d_out, extra_addend=None):
     """d_out: gradient w.r.t. the block output (consumed / overwritten).  extra_addend: gradient that reaches
     the block INPUT from elsewhere (decoder skip connection) -- folded into the dgrad epilogue chain.
     Returns gradient w.r.t. the block input."""
-    x = r["x"]
+    x, G = r["x"], r["G"]
     if blk.bottleneck:
-        dh2, dres = _conv_bn_bwd(d_out, r["out"], r["y3"], r["s3"], r["h2"], blk.conv3, blk.bn3, 1, 0, True, True, True)
-        dh1, _ = _conv_bn_bwd(dh2, r["h2"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, blk.stride, 1, True, False, True)
+        dh2, dres = _conv_bn_bwd(d_out, r["out"], r["y3"], r["s3"], r["h2"], blk.conv3, blk.bn3, 1, 0, True, True, True, None, G)
+        dh1, _ = _conv_bn_bwd(dh2, r["h2"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, blk.stride, 1, True, False, True, None, G)
         first = (dh1, r["h1"], r["y1"], r["s1"], blk.conv1, blk.bn1, 1, 0)
     else:
-        dh1, dres = _conv_bn_bwd(d_out, r["out"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, 1, 1, True, True, True)
+        dh1, dres = _conv_bn_bwd(d_out, r["out"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, 1, 1, True, True, True, None, G)
         first = (dh1, r["h1"], r["y1"], r["s1"], blk.conv1, blk.bn1, blk.stride, 1)
     if blk.downsample is not None:
         d_sc, _ = _conv_bn_bwd(dres, None, r["yd"], r["sd"], x, blk.downsample[0], blk.downsample[1], blk.stride, 0, False,
-                               False, True, extra_addend)
+                               False, True, extra_addend, G)
     else:
         d_sc = dres
         if extra_addend is not None:
             d_sc = d_sc + extra_addend          # not reached by ResNet-18/50 (skips feed downsample blocks)
     dz, z, y, s, conv, bn, st, pd = first
-    dx, _ = _conv_bn_bwd(dz, z, y, s, x, conv, bn, st, pd, True, False, True, d_sc)
+    dx, _ = _conv_bn_bwd(dz, z, y, s, x, conv, bn, st, pd, True, False, True, d_sc, G)
     return dx
 
 
-def encoder_forward(enc, x_nhwc, training):
+def encoder_forward(enc, x_nhwc, training, G=1):
     t = enc.encoder
-    rec = {"x": x_nhwc}
-    rec["y0"], f0, rec["s0"] = _conv_bn(x_nhwc, t.conv1, t.bn1, 2, 3, training, True)
+    rec = {"x": x_nhwc, "G": G}
+    rec["y0"], f0, rec["s0"] = _conv_bn(x_nhwc, t.conv1, t.bn1, 2, 3, training, True, None, G)
     rec["f0"] = f0
     pooled, rec["pool_idx"] = O.maxpool_fwd(f0)
     feats, blocks, x = [f0], [], pooled
     for li in range(1, 5):
         for blk in getattr(t, "layer%d" % li):
-            r, x = block_forward(blk, x, training)
+            r, x = block_forward(blk, x, training, G)
             blocks.append((blk, r))
         feats.append(x)
     rec["blocks"], rec["feats"] = blocks, feats
@@ -390,7 +392,7 @@ def encoder_backward(enc, rec, d_feats):
     else:
         d_f0 = torch.empty_like(f0)
         O.maxpool_bwd(d, rec["pool_idx"], f0.shape, d_f0, False)
-    _conv_bn_bwd(d_f0, f0, rec["y0"], rec["s0"], rec["x"], t.conv1, t.bn1, 2, 3, True, False, False)
+    _conv_bn_bwd(d_f0, f0, rec["y0"], rec["s0"], rec["x"], t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -411,15 +413,28 @@ class DispResNet(ArenaNet):
         self.ensure_arena()
         if torch.is_grad_enabled():
             self._pending += 1
-        outs = _NetCall.apply(self, self._hook, x)
+        outs = _NetCall.apply(self, self._hook, 1, x)
         return list(outs) if self.training else outs[0]
 
+    def forward_multi(self, images):
+        """Several independent network calls in ONE launch sequence: `images` is a list of [B,3,H,W] tensors;
+        returns one output per image, each exactly what `self(image)` would return.  The calls are stacked on
+        the batch axis (more rows per GEMM, 1/len(images) of the kernel launches) while BatchNorm statistics
+        and running-stat updates stay per call, in list order (train.py:427-434 semantics)."""
+        self.ensure_arena()
+        if torch.is_grad_enabled():
+            self._pending += 1
+        G, B = len(images), images[0].shape[0]
+        outs = _NetCall.apply(self, self._hook, G, torch.cat(list(images), 0))
+        per = [[o[g * B:(g + 1) * B] for o in outs] for g in range(G)]
+        return per if self.training else [p[0] for p in per]
+
     # -- forward ------------------------------------------------------------------------------
-    def _forward_impl(self, x):
+    def _forward_impl(self, groups, x):
         from . import lib as L
         x = L.dev_f32(x, "DispResNet input")
         training = self.training
-        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(x), training)
+        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(x), training, groups)
         dec = self.decoder
         rec = {"enc": enc_rec, "stages": {}}
         cur = feats[4]
@@ -503,12 +518,22 @@ class PoseResNet(ArenaNet):
         self.ensure_arena()
         if torch.is_grad_enabled():
             self._pending += 1
-        return _NetCall.apply(self, self._hook, img1, img2)[0]
+        return _NetCall.apply(self, self._hook, 1, img1, img2)[0]
 
-    def _forward_impl(self, img1, img2):
+    def forward_multi(self, pairs):
+        """`pairs` = list of (img1, img2); one stacked launch sequence, BatchNorm per call (see DispResNet.forward_multi).
+        Returns the list of [B,6] poses."""
+        self.ensure_arena()
+        if torch.is_grad_enabled():
+            self._pending += 1
+        G, B = len(pairs), pairs[0][0].shape[0]
+        out = _NetCall.apply(self, self._hook, G, torch.cat([a for a, _ in pairs], 0), torch.cat([b for _, b in pairs], 0))[0]
+        return [out[g * B:(g + 1) * B] for g in range(G)]
+
+    def _forward_impl(self, groups, img1, img2):
         from . import lib as L
         img1, img2 = L.dev_f32(img1, "PoseResNet input"), L.dev_f32(img2, "PoseResNet input")
-        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(img1, img2), self.training)
+        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(img1, img2), self.training, groups)
         n = self.decoder.net
         rec = {"enc": enc_rec, "f4": feats[4]}
         rec["s"] = O.conv_fwd(feats[4], n[0].w_khwc(), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU)
@@ -537,31 +562,61 @@ class ArenaAdam:
     """torch.optim.Adam semantics (betas, eps 1e-8, weight decay folded into the gradient) with one kernel
     launch per network.  Parameters whose gradient stays zero (the unused fc head and, with
     --num-scales 1, the scale 1-3 disparity heads) are left unchanged exactly as Adam skips
-    `grad is None` parameters in the reference."""
+    `grad is None` parameters in the reference.  The step counter lives on the device so that the whole
+    training step can be captured in a CUDA graph."""
 
     def __init__(self, nets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.nets = list(nets)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.state = {}
-        self.step_count = 0
+        self._step = None
+
+    @property
+    def step_count(self):
+        return 0 if self._step is None else int(self._step.item())
 
     def zero_grad(self, set_to_none=False):
         for n in self.nets:
             n.ensure_arena()
             n.zero_grad()
 
-    def step(self):
-        self.step_count += 1
+    def _ensure_state(self):
         for n in self.nets:
             n.ensure_arena()
             key = id(n)
             if key not in self.state or self.state[key][2] is not n._flat:      # first step, or the arena was re-packed
                 self.state[key] = (torch.zeros_like(n._flat), torch.zeros_like(n._flat), n._flat)
-            m, v, _ = self.state[key]
+        if self._step is None:
+            self._step = torch.zeros(1, device=self.nets[0]._flat.device, dtype=torch.int32)
+
+    def step(self):
+        self._ensure_state()
+        self._step += 1
+        for n in self.nets:
+            m, v, _ = self.state[id(n)]
             O.adam_step(n._flat, n._flat_grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                        self.step_count)
+                        0, self._step)
         O.invalidate_weight_cache()        # flipped dgrad weights are stale after the update
 
+    def snapshot(self):
+        """Copies of everything a step mutates (used to undo the warm-up step before CUDA-graph capture)."""
+        self._ensure_state()
+        snap = {"step": self._step.clone(), "nets": []}
+        for n in self.nets:
+            m, v, _ = self.state[id(n)]
+            snap["nets"].append((n._flat.clone(), m.clone(), v.clone(), {k: b.clone() for k, b in n.named_buffers()}))
+        return snap
+
+    def restore(self, snap):
+        self._step.copy_(snap["step"])
+        for n, (flat, m0, v0, bufs) in zip(self.nets, snap["nets"]):
+            m, v, _ = self.state[id(n)]
+            n._flat.copy_(flat); m.copy_(m0); v.copy_(v0)
+            for k, b in n.named_buffers():
+                b.copy_(bufs[k])
+        O.invalidate_weight_cache()
+
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": [self.state[id(n)][0] for n in self.nets if id(n) in self.state],
-                "exp_avg_sq": [self.state[id(n)][1] for n in self.nets if id(n) in self.state]}
+        self._ensure_state()
+        return {"step": self.step_count, "exp_avg": [self.state[id(n)][0] for n in self.nets],
+                "exp_avg_sq": [self.state[id(n)][1] for n in self.nets]}

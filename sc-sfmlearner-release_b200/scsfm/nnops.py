@@ -52,7 +52,7 @@ def _lib():
         lib.scsfm_act_bwd.argtypes = [P, P, LL, I, P]
         lib.scsfm_spatial_mean_fwd.argtypes = [P, I, I, I, F, P, P]
         lib.scsfm_spatial_mean_bwd.argtypes = [P, I, I, I, F, P, P]
-        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P]
+        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P]
         _bound = True
     return lib
 
@@ -74,6 +74,8 @@ def tc_supported(kind, Cin, Cout, kh, stride):
         return Cin % 4 == 0 and Cout >= 16
     if kind == "dgrad":                      # forward kernel on dout: its "Cin" is Cout, its "Cout" is Cin
         return stride == 1 and Cout % 4 == 0 and Cin >= 16
+    if kind == "wgrad":
+        return Cin % 4 == 0 and Cout % 4 == 0 and Cout >= 16
     return False
 
 
@@ -107,6 +109,11 @@ def conv_desc(x_shape, w, stride, pad, pad_mode, act):
                 stride, pad, pad_mode, act)
 
 
+def _tag(d):
+    if L.PROF["enabled"]:
+        L.TAG["next"] = "B%d %dx%d C%d->%d k%d s%d -> %dx%d" % (d.B, d.Hi, d.Wi, d.Cin, d.Cout, d.kh, d.stride, d.Ho, d.Wo)
+
+
 def _flops(d):
     """Algorithmic FLOPs of one conv pass: 2 * (B*Ho*Wo) * Cout * (kh*kw*Cin)."""
     return 2.0 * d.B * d.Ho * d.Wo * d.Cout * d.kh * d.kw * d.Cin
@@ -120,6 +127,7 @@ def conv_fwd(x, w, bias=None, stride=1, pad=0, pad_mode=PAD_ZERO, act=ACT_NONE, 
     d.inp, d.bias, d.out, d.bn_sums, d.bn_groups = x.data_ptr(), bias.data_ptr() if bias is not None else None, \
         y.data_ptr(), bn_sums.data_ptr() if bn_sums is not None else None, bn_groups
     tc = _use_tc("fwd", d.Cin, d.Cout, d.kh, stride)
+    _tag(d)
     fn = lib.scsfm_conv2d_fwd_tc if tc else lib.scsfm_conv2d_fwd_simt
     L.launch(fn, "scsfm_conv2d_fwd", "conv_fwd_tc" if tc else "conv_fwd_simt", 1, _flops(d), ctypes.byref(d), L.stream())
     return y
@@ -137,6 +145,7 @@ def conv_dgrad(dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=Fals
     din = empty((B, Hi, Wi, Cin), dout)
     d.dout, d.din, d.addend = dout.data_ptr(), din.data_ptr(), addend.data_ptr() if addend is not None else None
     tc = _use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
+    _tag(d)
     if tc:
         d.w = flipped_weights(w).data_ptr()
     fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
@@ -152,6 +161,7 @@ def conv_wgrad(x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
     d.inp, d.dout, d.dw, d.dbias = x.data_ptr(), dout.data_ptr(), dw.data_ptr(), dbias.data_ptr() if dbias is not None else None
     d.w = None
     tc = _use_tc("wgrad", d.Cin, d.Cout, d.kh, stride)
+    _tag(d)
     fn = lib.scsfm_conv2d_wgrad_tc if tc else lib.scsfm_conv2d_wgrad_simt
     L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
              ctypes.byref(d), L.stream())
@@ -256,6 +266,6 @@ def spatial_mean_bwd(dout, x_shape, scale):
     return dx
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
     L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, 28.0 * param.numel(), L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr, beta1,
-                                   beta2, eps, weight_decay, step, L.stream())
+                                   beta2, eps, weight_decay, step, L.ptr(step_dev), L.stream())

@@ -13,18 +13,20 @@ from .nets import ArenaAdam
 
 
 def compute_depth(disp_net, tgt_img, ref_imgs):
-    """train.py:426-434 -- depth = 1/disparity for the target and every reference, one network call each
-    (BatchNorm statistics stay per call)."""
-    tgt_depth = [1 / d for d in disp_net(tgt_img)]
-    ref_depths = [[1 / d for d in disp_net(r)] for r in ref_imgs]
-    return tgt_depth, ref_depths
+    """train.py:426-434 -- depth = 1/disparity for the target and every reference.  The 1 + len(ref_imgs) network
+    calls run as one stacked launch sequence (BatchNorm statistics and running-stat updates stay per call)."""
+    outs = disp_net.forward_multi([tgt_img] + list(ref_imgs))
+    depths = [[1 / d for d in o] for o in outs]
+    return depths[0], depths[1:]
 
 
 def compute_pose_with_inv(pose_net, tgt_img, ref_imgs):
-    """train.py:437-444."""
-    poses = [pose_net(tgt_img, r) for r in ref_imgs]
-    poses_inv = [pose_net(r, tgt_img) for r in ref_imgs]
-    return poses, poses_inv
+    """train.py:437-444 -- the reference's call order is (tgt,ref0), (ref0,tgt), (tgt,ref1), (ref1,tgt), ..."""
+    pairs = []
+    for r in ref_imgs:
+        pairs += [(tgt_img, r), (r, tgt_img)]
+    out = pose_net.forward_multi(pairs)
+    return out[0::2], out[1::2]
 
 
 class Trainer:
@@ -40,6 +42,8 @@ class Trainer:
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.exchange = None
+        self._graph = None
+        self.launches_per_step = None
         if self.distributed:
             self.exchange = GradExchange(self.world, torch.cuda.Stream())
             for net in (disp_net, pose_net):
@@ -62,7 +66,45 @@ class Trainer:
 
     def step(self, tgt_img, ref_imgs, intrinsics):
         """train.py:259-282 without a single host synchronisation; returns device scalars
-        (loss, photo, smooth, geometry)."""
+        (loss, photo, smooth, geometry).  After `capture()` the step is one CUDA-graph replay."""
+        if self._graph is not None:
+            self._static[0].copy_(tgt_img, non_blocking=True)
+            for dst, src in zip(self._static[1], ref_imgs):
+                dst.copy_(src, non_blocking=True)
+            self._static[2].copy_(intrinsics, non_blocking=True)
+            self._graph.replay()
+            return tuple(self._static_out.unbind(0))
+        return self._eager_step(tgt_img, ref_imgs, intrinsics)
+
+    def capture(self, tgt_img, ref_imgs, intrinsics):
+        """Record the whole step (7 network calls forward + backward, losses, Adam) into one CUDA graph: ~2500
+        kernel launches become a single graph launch.  One eager warm-up step runs first (lazy allocations,
+        Adam state) and is undone, so capturing does not advance training.  Single-GPU path."""
+        from . import lib as L
+        from . import nnops
+        if self.exchange is not None:
+            raise RuntimeError("graph capture of the data-parallel step is not enabled")
+        self._static = (tgt_img.clone(), [r.clone() for r in ref_imgs], intrinsics.clone())
+        snap = self.optimizer.snapshot()
+        prof = dict(L.PROF)
+        L.PROF.update(enabled=False)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._eager_step(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self.optimizer.restore(snap)
+        nnops.invalidate_weight_cache()
+        before = L.STATS["launches"]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._static_out = torch.stack(self._eager_step(*self._static))
+        self.launches_per_step = L.STATS["launches"] - before
+        nnops.invalidate_weight_cache()     # tensors cached during capture belong to the graph's private pool
+        self._graph = graph
+        L.PROF.update(prof)
+
+    def _eager_step(self, tgt_img, ref_imgs, intrinsics):
         loss, photo, smooth, geo = self.losses(tgt_img, ref_imgs, intrinsics)
         self.optimizer.zero_grad()
         loss.backward()

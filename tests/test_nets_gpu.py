@@ -208,12 +208,14 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind):
         rl.backward()
         return {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
     g64, g32 = oracle_grads(torch.float64), oracle_grads(torch.float32)
-    worst, worst_ref = 0.0, 0.0
-    for k, gr in g64.items():
-        e, e_ref = rel_l2(grads[k], gr), rel_l2(g32[k], gr)
-        worst, worst_ref = max(worst, e), max(worst_ref, e_ref)
-        assert e < 3 * e_ref + 1e-3, (k, e, e_ref)
-    print(tag, "worst per-parameter gradient rel-L2 vs fp64 oracle: %.2e (fp32 CPU oracle's own: %.2e)" % (worst, worst_ref))
+    errs = sorted((rel_l2(grads[k], gr), k) for k, gr in g64.items())
+    errs_ref = sorted(rel_l2(g32[k], gr) for k, gr in g64.items())
+    med, worst = errs[len(errs) // 2][0], errs[-1]
+    print(tag, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle's own: median %.2e worst %.2e"
+          % (med, worst[0], worst[1], errs_ref[len(errs_ref) // 2], errs_ref[-1]))
+    # systematic accuracy = the median (must be fp32-noise level); individual parameters may see a ReLU/ELU gate flip on an
+    # activation that is ~0 in one evaluation and ~-0 in the other (any independent fp32 evaluation does), hence the looser worst bound
+    assert med < 1e-4 and worst[0] < 3e-2
     sd2 = net.state_dict()
     rn = np.array([float(sd2[k].double().norm()) for k in g[f"{tag}_running_names"]])
     np.testing.assert_allclose(rn, g[f"{tag}_running_norms"], rtol=1e-4)
@@ -291,13 +293,15 @@ TC_CASES = [
     (2, 16, 28, 128, 256, 3, 1, 1, 0, 0, False),   # BN 64/128 dispatch
     (2, 9, 13, 256, 64, 1, 1, 0, 0, 0, False),     # bottleneck 1x1
     (2, 9, 13, 64, 256, 1, 1, 0, 0, 1, True),      # 1x1 expand + ReLU + bias
+    (4, 64, 104, 64, 128, 3, 1, 1, 0, 0, False),   # large M -> 128-wide N tile (3-stage pipeline)
+    (3, 64, 104, 128, 256, 1, 1, 0, 0, 0, False),  # 128-wide tile, two N tiles
 ]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
     """TF32 tensor-core kernels: inputs rounded to 10-bit mantissas by the hardware, fp32 accumulation.
-    Tolerance 2e-3 relative L2 (TF32 products have ~2^-11 relative error per operand)."""
+    Operands are rounded to nearest TF32 in the loaders: expected relative L2 error ~3e-4; bound 1e-3."""
     from scsfm import lib as L
     O = _ops()
     if not hasattr(L.load(), "scsfm_conv2d_fwd_tc"):
@@ -320,11 +324,19 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
         assert O._use_tc("fwd", Cin, Cout, k, stride)
         sums = torch.zeros(O.BN_SLOTS * Cout * 2, device=DEV, dtype=torch.float64)
         yc = O.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1)
-        assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < 2e-3
+        assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < 1e-3
         s = sums.view(O.BN_SLOTS, Cout, 2).sum(0).cpu()
         np.testing.assert_allclose(s[:, 0], yc.double().sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
         np.testing.assert_allclose(s[:, 1], (yc.double() ** 2).sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
         dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+        if hasattr(L.load(), "scsfm_conv2d_wgrad_tc"):
+            assert O._use_tc("wgrad", Cin, Cout, k, stride)
+            dw = torch.zeros_like(wc)
+            db = torch.zeros(Cout, device=DEV) if bias else None
+            O.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
+            assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 1e-3
+            if bias:
+                assert rel_l2(db, b.grad) < 1e-5
         if stride == 1:
             assert O._use_tc("dgrad", Cin, Cout, k, stride)
             O.invalidate_weight_cache()
@@ -371,3 +383,70 @@ def test_disp_net_tf32_mode_vs_oracle(golden_nets):
     finally:
         O.CONFIG["conv_mode"] = old
         O.invalidate_weight_cache()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_forward_multi_equals_separate_calls(mode):
+    """Stacking the 3 DispResNet / 4 PoseResNet calls of a training step into one launch sequence must not change
+    anything: per-call BatchNorm statistics, running-stat updates in call order, outputs, parameter gradients."""
+    import models
+    O = _ops()
+    old = O.CONFIG["conv_mode"]
+    O.CONFIG["conv_mode"] = mode
+    try:
+        imgs = [det_image(n, 2, 64, 96).to(DEV) for n in ("img1", "img2", "img3")]
+        tol = 1e-5 if mode == "fp32" else 2e-5     # identical kernels and inputs; only atomics order differs
+        for kind in ("disp", "pose"):
+            a, b = _build(kind, 18), _build(kind, 18)
+            a.train(); b.train()
+            if kind == "disp":
+                outs_a = [a(x) for x in imgs]
+                outs_b = b.forward_multi(imgs)
+                la = sum((1 / o[0]).mean() * (i + 1) for i, o in enumerate(outs_a))
+                lb = sum((1 / o[0]).mean() * (i + 1) for i, o in enumerate(outs_b))
+                for oa, ob in zip(outs_a, outs_b):
+                    for s in range(4):
+                        assert rel_l2(ob[s], oa[s]) < tol
+            else:
+                pairs = [(imgs[0], imgs[1]), (imgs[1], imgs[0]), (imgs[0], imgs[2]), (imgs[2], imgs[0])]
+                outs_a = [a(x, y) for x, y in pairs]
+                outs_b = b.forward_multi(pairs)
+                wts = torch.arange(1, 7, device=DEV, dtype=torch.float32)
+                la = sum((o * wts).sum() * (i + 1) for i, o in enumerate(outs_a)) * 100
+                lb = sum((o * wts).sum() * (i + 1) for i, o in enumerate(outs_b)) * 100
+                for oa, ob in zip(outs_a, outs_b):
+                    assert rel_l2(ob, oa) < 10 * tol
+            la.backward(); lb.backward()
+            assert rel_l2(b.flat_grads(), a.flat_grads()) < (1e-4 if mode == "fp32" else 1e-3)
+            sa, sb = a.state_dict(), b.state_dict()
+            for k in sa:
+                if "running" in k:
+                    assert rel_l2(sb[k], sa[k]) < 1e-5, k
+                if "num_batches_tracked" in k:
+                    assert int(sa[k]) == int(sb[k]) == (3 if kind == "disp" else 4)
+    finally:
+        O.CONFIG["conv_mode"] = old
+        O.invalidate_weight_cache()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("shape", [(6, 4, 6, 64, 3), (6, 8, 12, 64, 3), (8, 16, 24, 128, 4), (3, 5, 7, 32, 3)])
+def test_fused_batchnorm_sums_per_group(mode, shape):
+    """Per-group BatchNorm partial sums out of the conv epilogue when several calls are stacked: groups whose
+    row ranges straddle the 128-row (tensor-core) / 64-row (CUDA-core) tiles."""
+    O = _ops()
+    B, H, W, C, G = shape
+    old = O.CONFIG["conv_mode"]
+    O.CONFIG["conv_mode"] = mode
+    try:
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, H, W, C, generator=g).to(DEV)
+        w = (torch.randn(C, 3, 3, C, generator=g) / (9 * C) ** 0.5).to(DEV)
+        sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=DEV, dtype=torch.float64)
+        y = O.conv_fwd(x, w, None, 1, 1, O.PAD_ZERO, O.ACT_NONE, sums, G)
+        got = sums.view(O.BN_SLOTS, G, C, 2).sum(0)
+        yg = y.double().view(G, -1, C)
+        np.testing.assert_allclose(got[..., 0].cpu(), yg.sum(1).cpu(), rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(got[..., 1].cpu(), (yg ** 2).sum(1).cpu(), rtol=1e-5, atol=1e-4)
+    finally:
+        O.CONFIG["conv_mode"] = old

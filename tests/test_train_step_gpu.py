@@ -74,3 +74,31 @@ def test_step_issues_no_host_synchronisation():
     finally:
         torch.cuda.set_sync_debug_mode("default")
     torch.cuda.synchronize()
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """Trainer.capture(): the whole step as one CUDA graph.  Three replayed steps must track three eager steps
+    (same weights, same data) and capturing itself must not advance training."""
+    import models
+    from scsfm import synth
+    from scsfm.trainer import Trainer
+    tgt, refs, K = synth.triplet(2, 2, 96, 160)
+    args = (tgt.to(DEV), [r.to(DEV) for r in refs], K.to(DEV))
+
+    def make():
+        d, p = models.DispResNet(18, False), models.PoseResNet(18, False)
+        d.load_state_dict(det_weights(d.state_dict())); p.load_state_dict(det_weights(p.state_dict()))
+        return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=0, distributed=False)
+    eager, graphed = make(), make()
+    w0 = graphed.disp_net.flat_params().clone()
+    graphed.capture(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(graphed.disp_net.flat_params(), w0)          # warm-up step undone
+    assert graphed.optimizer.step_count == 0
+    assert graphed.launches_per_step > 300
+    for it in range(3):
+        a = [float(v) for v in eager.step(*args)]
+        b = [float(v) for v in graphed.step(*args)]
+        np.testing.assert_allclose(b, a, rtol=2e-4 if it == 0 else 5e-3)
+    assert graphed.optimizer.step_count == 3
+    assert float((graphed.disp_net.flat_params() - eager.disp_net.flat_params()).abs().max()) <= 6.1e-4   # 3 steps x 2 lr

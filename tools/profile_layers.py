@@ -1,0 +1,44 @@
+"""Per-launch CUDA-event profile of one training step: every conv call with its shape, time, TFLOP/s.
+Usage: python tools/profile_layers.py [fp32|tf32]"""
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sc-sfmlearner-release_b200"))
+import torch  # noqa: E402
+
+import models  # noqa: E402
+from scsfm import lib as L, nnops, synth  # noqa: E402
+from scsfm.trainer import Trainer  # noqa: E402
+
+
+def main():
+    nnops.CONFIG["conv_mode"] = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+    dev = "cuda"
+    tr = Trainer(models.DispResNet(18, False).to(dev).train(), models.PoseResNet(18, False).to(dev).train(),
+                 with_auto_mask=1, distributed=False)
+    tgt, refs, K = synth.triplet(0, 4, 256, 832)
+    args = (tgt.to(dev), [r.to(dev) for r in refs], K.to(dev))
+    for _ in range(2):
+        tr.step(*args)
+    torch.cuda.synchronize()
+    L.PROF.update(enabled=True, only=None, events=[])
+    tr.step(*args)
+    torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    for fam, work, e0, e1, tag in L.PROF["events"]:
+        key = (fam, tag)
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += work
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    total = sum(v[1] for v in agg.values())
+    print("total profiled %.2f ms" % total)
+    for (fam, tag), (n, ms, work) in rows[:70]:
+        rate = work / (ms * 1e-3) / 1e12 if fam.startswith("conv") else work / (ms * 1e-3) / 1e9
+        unit = "TF/s" if fam.startswith("conv") else "GB/s"
+        print("%-16s %-40s n=%3d %8.3f ms %8.1f %s" % (fam, tag or "", n, ms, rate, unit))
+
+
+if __name__ == "__main__":
+    main()
