@@ -139,6 +139,9 @@ int scsfm_smooth_bwd(const ScsfmSmoothJob* jobs_host, int njobs, int B, int H, i
 #define SCSFM_ACT_ELU 2           /* nn.ELU, DispResNet.py:20 */
 #define SCSFM_ACT_DISP 3          /* 10*sigmoid(x)+0.01, DispResNet.py:98 */
 #define SCSFM_BN_SLOTS 16
+/* OR-ed into an `act` / `relu` argument: round the stored result to TF32 (round-to-nearest-away, cvt.rna) so that the
+ * tensor-core loaders can consume it without converting (the MMA would otherwise truncate the low 13 mantissa bits) */
+#define SCSFM_ROUND_TF32 0x100
 
 typedef struct ScsfmConv {
     /* forward operands */
@@ -215,6 +218,9 @@ int scsfm_act_bwd(float* d, const float* out, long long n, int act, void* stream
 /* pose head (PoseResNet.py:47-49): out[b,c] = scale * mean_hw x[b,hw,c]; backward broadcasts. */
 int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, float scale, float* out, void* stream);
 int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream);
+
+/* out[i] = round-to-nearest TF32 of in[i] (weights of the tensor-core convolutions, once per optimizer step) */
+int scsfm_round_tf32(const float* in, float* out, long long n, void* stream);
 
 /* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena.  The 1-based step count is
  * `step`, or *step_dev (device int) when step_dev != NULL so that a captured CUDA graph stays valid. */

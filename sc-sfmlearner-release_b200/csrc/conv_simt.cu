@@ -82,7 +82,7 @@ struct GatherIn {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-    switch (act) {
+    switch (act & 0xff) {
         case ACT_RELU: return fmaxf(v, 0.f);
         case ACT_ELU: return v > 0.f ? v : expm1f(v);
         case ACT_DISP: return 10.0f * (1.0f / (1.0f + expf(-v))) + 0.01f;   // alpha*sigmoid+beta, DispResNet.py:98
@@ -186,6 +186,7 @@ conv_fwd_simt_kernel(ScsfmConv p) {
             if (n < N) {
                 if (p.bias) x += __ldg(p.bias + n);
                 x = apply_act(x, p.act);
+                if (p.act & ROUND_TF32) x = tf32_round(x);
                 if (want_stats) {
                     if (uniform_group) { csum[j] += (double)x; csq[j] += (double)x * (double)x; }
                     else {

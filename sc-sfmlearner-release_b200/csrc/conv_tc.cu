@@ -34,17 +34,14 @@ struct TcCfg {
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 };
 
-// fp32 -> tf32 with round-to-nearest (the tensor core would otherwise TRUNCATE the low 13 mantissa bits, a
-// systematic -7e-4 relative bias on every dot product; measured in tools/debug_tc.py)
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+// Operand precision: kind::tf32 TRUNCATES the low 13 mantissa bits of whatever fp32 pattern sits in shared memory
+// (measured: a systematic -7e-4 relative bias per dot product).  Converting with cvt.rna inside the loaders costs
+// ~50% of the loader-bound kernel time, so the operands are rounded ONCE where they are produced instead: every
+// kernel that writes a tensor later consumed by a convolution takes the SCSFM_ROUND_TF32 flag, and the weights are
+// rounded per optimizer step (scsfm_round_tf32).  The loaders below therefore copy bits unchanged.
 
 __device__ __forceinline__ float tc_act(float v, int act) {
-    switch (act) {
+    switch (act & 0xff) {
         case ACT_RELU: return fmaxf(v, 0.f);
         case ACT_ELU: return v > 0.f ? v : expm1f(v);
         case ACT_DISP: return 10.0f * (1.0f / (1.0f + expf(-v))) + 0.01f;
@@ -139,9 +136,9 @@ conv_fwd_tc_kernel(ScsfmConv p) {
             uint8_t* a_st = sA + s * A_STAGE_BYTES + cs * 16;
             uint8_t* b_st = sB + s * Cfg::B_STAGE_BYTES + cs * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = tf32_rn4(va[i]);
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = va[i];
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = tf32_rn4(vb[j]);
+            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = vb[j];
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_full + s);
             // advance this thread's K index by one k-block
@@ -176,6 +173,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
                     if (p.bias) x += __ldg(p.bias + n);
                     if (p.addend) x += __ldg(p.addend + (size_t)m * N + n);
                     x = tc_act(x, p.act);
+                    if (p.act & ROUND_TF32) x = tf32_round(x);
                 } else {
                     x = 0.f;
                 }
@@ -268,7 +266,7 @@ __global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int T, i
         const int o = (int)(i % Co);
         const long long t2 = i / Co;
         const int tap = (int)(t2 % T), c = (int)(t2 / T);
-        wt[i] = __ldg(w + ((size_t)o * T + (T - 1 - tap)) * Ci + c);
+        wt[i] = tf32_round(__ldg(w + ((size_t)o * T + (T - 1 - tap)) * Ci + c));   // operand of the tensor-core dgrad
     }
 }
 
@@ -392,12 +390,12 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int k = kr0 + 4 * i;                  // pixel row inside the block: group k/4, row k%4
-                *reinterpret_cast<float4*>(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16)) = tf32_rn4(va[i]);
+                *reinterpret_cast<float4*>(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16)) = va[i];
             }
 #pragma unroll
             for (int i = 0; i < B_IT; ++i) {
                 const int k = b_kr0 + (128 / BCH) * i;
-                *reinterpret_cast<float4*>(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16)) = tf32_rn4(vb[i]);
+                *reinterpret_cast<float4*>(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16)) = vb[i];
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_full + s);

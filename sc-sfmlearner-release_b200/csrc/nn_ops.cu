@@ -101,9 +101,13 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
             const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + i);
             o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
         }
-        if (relu) {
+        if (relu & 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        if (relu & ROUND_TF32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = tf32_round(o[j]);
         }
         reinterpret_cast<float4*>(z)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -137,7 +141,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
             const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
             float d[4] = {d4.x, d4.y, d4.z, d4.w};
             const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-            if (relu) {
+            if (relu & 1) {
                 const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
                 if (!(z4.x > 0.f)) d[0] = 0.f;
                 if (!(z4.y > 0.f)) d[1] = 0.f;
@@ -187,7 +191,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
         const float4 y4 = __ldg(reinterpret_cast<const float4*>(y) + i);
         float d[4] = {d4.x, d4.y, d4.z, d4.w};
         const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-        if (relu) {
+        if (relu & 1) {
             const float4 z4 = __ldg(reinterpret_cast<const float4*>(z) + i);
             const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
@@ -201,6 +205,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
             const double* w = work + ((size_t)g * C + c + j) * 2;
             const float xhat = (yy[j] - sv[2]) * sv[3];
             o[j] = sv[0] * (d[j] - (float)w[0] * inv_n - xhat * (float)w[1] * inv_n);
+            if (relu & ROUND_TF32) o[j] = tf32_round(o[j]);
         }
         if (dres) reinterpret_cast<float4*>(dres)[i] = make_float4(d[0], d[1], d[2], d[3]);
         reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -309,7 +314,7 @@ __global__ void upcat_fwd_kernel(const float* __restrict__ lo, const float* __re
 }
 
 __device__ __forceinline__ float act_grad(float out, int act) {
-    switch (act) {
+    switch (act & 0xff) {
         case ACT_RELU: return out > 0.f ? 1.f : 0.f;
         case ACT_ELU: return out > 0.f ? 1.f : out + 1.f;          // d/dx elu = exp(x) = elu(x)+1 for x<=0
         case ACT_DISP: { const float s = (out - 0.01f) * 0.1f; return 10.f * s * (1.f - s); }
@@ -351,10 +356,11 @@ __global__ void fold_plain_kernel(const float* __restrict__ dpad, int B, int H, 
         float4 a = fold_at(dpad, b, h, w, H, W, C, c);
         float4* dst = reinterpret_cast<float4*>(d) + i;
         if (accumulate) { const float4 o = *dst; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
-        if (act != ACT_NONE) {
+        if ((act & 0xff) != ACT_NONE) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(act_out) + i);
             a.x *= act_grad(q.x, act); a.y *= act_grad(q.y, act); a.z *= act_grad(q.z, act); a.w *= act_grad(q.w, act);
         }
+        if (act & ROUND_TF32) { a.x = tf32_round(a.x); a.y = tf32_round(a.y); a.z = tf32_round(a.z); a.w = tf32_round(a.w); }
         *dst = a;
     }
 }
@@ -378,10 +384,11 @@ __global__ void fold_up_lo_kernel(const float* __restrict__ dpad, int B, int H, 
                 const float4 v = fold_at(dpad, b, 2 * h2 + dy, 2 * w2 + dx, H, W, Ct, c);
                 a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
-        if (act != ACT_NONE) {
+        if ((act & 0xff) != ACT_NONE) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(lo_act) + i);
             a.x *= act_grad(q.x, act); a.y *= act_grad(q.y, act); a.z *= act_grad(q.z, act); a.w *= act_grad(q.w, act);
         }
+        if (act & ROUND_TF32) { a.x = tf32_round(a.x); a.y = tf32_round(a.y); a.z = tf32_round(a.z); a.w = tf32_round(a.w); }
         reinterpret_cast<float4*>(d_lo)[i] = a;
     }
 }
@@ -403,7 +410,7 @@ __global__ void fold_up_skip_kernel(const float* __restrict__ dpad, int B, int H
 
 __global__ void act_bwd_kernel(float* __restrict__ d, const float* __restrict__ out, long long n, int act) {
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT)
-        d[i] *= act_grad(__ldg(out + i), act);
+        d[i] = maybe_round(d[i] * act_grad(__ldg(out + i), act), act & ROUND_TF32);
 }
 
 // ----- pose head --------------------------------------------------------------------------------
@@ -425,6 +432,11 @@ __global__ void spatial_mean_bwd_kernel(const float* __restrict__ dout, int B, i
         const int b = (int)(i / ((long long)HW * C));
         dx[i] = __ldg(dout + b * C + c) * k;
     }
+}
+
+// ----- TF32 rounding of a whole buffer (weights, once per optimizer step) ----------------------------
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) out[i] = tf32_round(__ldg(in + i));
 }
 
 // ----- Adam ---------------------------------------------------------------------------------------
@@ -495,7 +507,7 @@ extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y
     (void)gamma;
     SCSFM_CHECK_ARG(dz && y && saved && dy && work && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 && rows % groups == 0,
                     "bn_backward: bad arguments");
-    SCSFM_CHECK_ARG(!relu || z, "bn_backward: relu gate needs z");
+    SCSFM_CHECK_ARG(!(relu & 1) || z, "bn_backward: relu gate needs z");
     const long long rpg = rows / groups;
     SCSFM_CHECK_CUDA(cudaMemsetAsync(work, 0, (size_t)groups * C * 2 * sizeof(double), ST));
     const int slab4 = (C / 4) < NT ? (C / 4) : NT;
@@ -546,7 +558,7 @@ extern "C" int scsfm_upcat_fwd(const float* lo, const float* skip, int B, int H,
 extern "C" int scsfm_fold_bwd(const float* dpad, int B, int H, int W, int C1, int C2, int upsample, float* d_lo,
                               const float* lo_act, int act, int accumulate, float* d_skip, void* stream) {
     SCSFM_CHECK_ARG(dpad && d_lo && B > 0 && H >= 2 && W >= 2 && C1 > 0 && (C1 & 3) == 0 && C2 >= 0 && (C2 & 3) == 0, "fold_bwd: bad arguments");
-    SCSFM_CHECK_ARG(act == ACT_NONE || lo_act, "fold_bwd: activation gradient needs the activation output");
+    SCSFM_CHECK_ARG((act & 0xff) == ACT_NONE || lo_act, "fold_bwd: activation gradient needs the activation output");
     if (!upsample) {
         SCSFM_CHECK_ARG(C2 == 0, "fold_bwd: concat without upsample is not used by the decoder");
         fold_plain_kernel<<<grid_for((long long)B * H * W * (C1 / 4)), NT, 0, ST>>>(dpad, B, H, W, C1, d_lo, lo_act, act, accumulate);
@@ -580,6 +592,13 @@ extern "C" int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, floa
 extern "C" int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream) {
     SCSFM_CHECK_ARG(dout && dx && B > 0 && HW > 0 && C > 0, "spatial_mean_bwd: bad arguments");
     spatial_mean_bwd_kernel<<<grid_for((long long)B * HW * C), NT, 0, ST>>>(dout, B, HW, C, scale, dx);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_round_tf32(const float* in, float* out, long long n, void* stream) {
+    SCSFM_CHECK_ARG(in && out && n > 0, "round_tf32: bad arguments");
+    round_tf32_kernel<<<grid_for(n), NT, 0, ST>>>(in, out, n);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

@@ -48,6 +48,11 @@ class ConvParams(nn.Module):
         """[Cout,kh,kw,Cin] contiguous view of the channels-last weight (no copy)."""
         return self.weight.permute(0, 2, 3, 1)
 
+    def w_op(self):
+        """Weights as the conv kernels' B operand: in tf32 mode the per-call TF32-rounded copy of the arena."""
+        tc = getattr(self, "_tc_view", None)
+        return tc if (tc is not None and O.CONFIG["conv_mode"] == "tf32") else self.w_khwc()
+
 
 class BNParams(nn.Module):
     def __init__(self, c):
@@ -224,6 +229,22 @@ class ArenaNet(nn.Module):
             off += _aligned(cnt)
         self._flat, self._flat_grad, self._views = flat, gflat, views
         self._hook = torch.zeros(1, device=dev, requires_grad=True)
+        # TF32-rounded mirror of the parameter arena (refreshed at the start of every network call in tf32 mode)
+        self._flat_tf32 = torch.zeros_like(flat)
+        off = 0
+        mods = {id(m.weight): m for m in self.modules() if isinstance(m, ConvParams)}
+        for p in params:
+            cnt = p.numel()
+            if p.dim() == 4 and id(p) in mods:
+                O_, I_, kh, kw = p.shape
+                mods[id(p)]._tc_view = self._flat_tf32[off:off + cnt].view(O_, kh, kw, I_)
+            off += _aligned(cnt)
+
+    def refresh_operand_weights(self):
+        """Start of every network call: the weights may have changed since the last one (optimizer, load_state_dict)."""
+        O.invalidate_weight_cache()
+        if O.CONFIG["conv_mode"] == "tf32":
+            O.round_tf32(self._flat, self._flat_tf32)
 
     def _attach_grads(self):
         """Called at the start of every backward: if an optimizer dropped the gradients
@@ -286,22 +307,22 @@ def _bn_fwd(y, sums, bn, training, relu, residual, groups):
     saved = O.bn_prepare(sums, groups, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, training)
     if training:
         bn.num_batches_tracked += groups
-    return O.bn_apply(y, saved, residual, relu, groups), saved
+    return O.bn_apply(y, saved, residual, (1 if relu else 0) | O.rnd(), groups), saved
 
 
 def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
     C = conv.weight.shape[0]
     sums = torch.zeros(O.BN_SLOTS * groups * C * 2, device=x.device, dtype=torch.float64) if training else None
-    y = O.conv_fwd(x, conv.w_khwc(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups)
+    y = O.conv_fwd(x, conv.w_op(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups)
     z, saved = _bn_fwd(y, sums, bn, training, relu, residual, groups)
     return y, z, saved
 
 
 def _conv_bn_bwd(dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None, groups=1):
     """Backward through relu?(bn(conv(x)) [+res]).  Returns (dx or None, dres or None)."""
-    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, relu, want_dres, groups)
+    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, (1 if relu else 0) | O.rnd(), want_dres, groups)
     O.conv_wgrad(x, dy, ArenaNet.g(conv.weight), None, stride, pad, O.PAD_ZERO)
-    dx = O.conv_dgrad(dy, conv.w_khwc(), x.shape, stride, pad, addend) if need_dx else None
+    dx = O.conv_dgrad(dy, conv.w_op(), x.shape, stride, pad, addend) if need_dx else None
     return dx, dres
 
 
@@ -321,7 +342,7 @@ def block_forward(blk, x, training, G=1):
         r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
     C = last_conv.weight.shape[0]
     sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=x.device, dtype=torch.float64) if training else None
-    y = O.conv_fwd(last_in, last_conv.w_khwc(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G)
+    y = O.conv_fwd(last_in, last_conv.w_op(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G)
     out, saved = _bn_fwd(y, sums, last_bn, training, True, sc, G)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
     return r, out
@@ -433,6 +454,7 @@ class DispResNet(ArenaNet):
     def _forward_impl(self, groups, x):
         from . import lib as L
         x = L.dev_f32(x, "DispResNet input")
+        self.refresh_operand_weights()
         training = self.training
         enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(x), training, groups)
         dec = self.decoder
@@ -442,14 +464,14 @@ class DispResNet(ArenaNet):
         for i in range(4, -1, -1):
             st = {"in0": cur}
             c0 = dec.up(i, 0)
-            st["a"] = O.conv_fwd(cur, c0.w_khwc(), c0.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU)
+            st["a"] = O.conv_fwd(cur, c0.w_op(), c0.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | O.rnd())
             st["cat"] = O.upcat_fwd(st["a"], feats[i - 1] if i > 0 else None)
             c1 = dec.up(i, 1)
-            st["b"] = O.conv_fwd(st["cat"], c1.w_khwc(), c1.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU)
+            st["b"] = O.conv_fwd(st["cat"], c1.w_op(), c1.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | O.rnd())
             cur = st["b"]
             if i < 4 and (training or i == 0):
                 dc = dec.disp(i)
-                disps[i] = O.conv_fwd(cur, dc.w_khwc(), dc.bias, 1, 1, O.PAD_REFLECT, O.ACT_DISP)
+                disps[i] = O.conv_fwd(cur, dc.w_op(), dc.bias, 1, 1, O.PAD_REFLECT, O.ACT_DISP)
             rec["stages"][i] = st
         rec["disps"] = disps
         order = [0, 1, 2, 3] if training else [0]
@@ -475,25 +497,25 @@ class DispResNet(ArenaNet):
                 disp = rec["disps"][i]
                 dpre = O.act_bwd_(d_disp[i].reshape(disp.shape).clone(), disp, O.ACT_DISP)
                 O.conv_wgrad(b, dpre, g(dc.weight), dc.bias.grad, 1, 1, O.PAD_REFLECT)
-                dpad = O.conv_dgrad(dpre, dc.w_khwc(), b.shape, 1, 1, None, padded_input=True)
+                dpad = O.conv_dgrad(dpre, dc.w_op(), b.shape, 1, 1, None, padded_input=True)
                 if not have:
                     d_b = torch.empty_like(b)
-                O.fold_plain(dpad, d_b, b, O.ACT_ELU, accumulate=have)
+                O.fold_plain(dpad, d_b, b, O.ACT_ELU | O.rnd(), accumulate=have)
             elif have:
-                O.act_bwd_(d_b, b, O.ACT_ELU)
+                O.act_bwd_(d_b, b, O.ACT_ELU | O.rnd())
             else:
                 continue            # nothing reaches this stage (cannot happen: stage 0 always has scale 0)
             # up(i,1): b = ELU(conv(reflect_pad(cat)))
             c1 = dec.up(i, 1)
             O.conv_wgrad(st["cat"], d_b, g(c1.weight), c1.bias.grad, 1, 1, O.PAD_REFLECT)
-            dpad = O.conv_dgrad(d_b, c1.w_khwc(), st["cat"].shape, 1, 1, None, padded_input=True)
-            d_a, d_skip = O.fold_upcat(dpad, st["a"].shape[-1], st["a"], O.ACT_ELU)
+            dpad = O.conv_dgrad(d_b, c1.w_op(), st["cat"].shape, 1, 1, None, padded_input=True)
+            d_a, d_skip = O.fold_upcat(dpad, st["a"].shape[-1], st["a"], O.ACT_ELU | O.rnd())
             if i > 0:
                 d_feats[i - 1] = d_skip
             # up(i,0): a = ELU(conv(reflect_pad(in0)))
             c0 = dec.up(i, 0)
             O.conv_wgrad(st["in0"], d_a, g(c0.weight), c0.bias.grad, 1, 1, O.PAD_REFLECT)
-            dpad = O.conv_dgrad(d_a, c0.w_khwc(), st["in0"].shape, 1, 1, None, padded_input=True)
+            dpad = O.conv_dgrad(d_a, c0.w_op(), st["in0"].shape, 1, 1, None, padded_input=True)
             d_in = torch.empty_like(st["in0"])
             O.fold_plain(dpad, d_in, None, O.ACT_NONE, accumulate=False)
             if i < 4:
@@ -533,13 +555,14 @@ class PoseResNet(ArenaNet):
     def _forward_impl(self, groups, img1, img2):
         from . import lib as L
         img1, img2 = L.dev_f32(img1, "PoseResNet input"), L.dev_f32(img2, "PoseResNet input")
+        self.refresh_operand_weights()
         enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(img1, img2), self.training, groups)
         n = self.decoder.net
         rec = {"enc": enc_rec, "f4": feats[4]}
-        rec["s"] = O.conv_fwd(feats[4], n[0].w_khwc(), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU)
-        rec["p0"] = O.conv_fwd(rec["s"], n[1].w_khwc(), n[1].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU)
-        rec["p1"] = O.conv_fwd(rec["p0"], n[2].w_khwc(), n[2].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU)
-        rec["p2"] = O.conv_fwd(rec["p1"], n[3].w_khwc(), n[3].bias, 1, 0, O.PAD_ZERO, O.ACT_NONE)
+        rec["s"] = O.conv_fwd(feats[4], n[0].w_op(), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU | O.rnd())
+        rec["p0"] = O.conv_fwd(rec["s"], n[1].w_op(), n[1].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | O.rnd())
+        rec["p1"] = O.conv_fwd(rec["p0"], n[2].w_op(), n[2].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | O.rnd())
+        rec["p2"] = O.conv_fwd(rec["p1"], n[3].w_op(), n[3].bias, 1, 0, O.PAD_ZERO, O.ACT_NONE)
         return rec, [O.spatial_mean_fwd(rec["p2"], 0.01)]
 
     def _backward_impl(self, rec, grads):
@@ -549,9 +572,9 @@ class PoseResNet(ArenaNet):
         chain = [(n[3], rec["p1"], 0), (n[2], rec["p0"], 1), (n[1], rec["s"], 1), (n[0], rec["f4"], 0)]
         for k, (conv, inp, pad) in enumerate(chain):
             O.conv_wgrad(inp, d, g(conv.weight), conv.bias.grad, 1, pad, O.PAD_ZERO)
-            d = O.conv_dgrad(d, conv.w_khwc(), inp.shape, 1, pad)
+            d = O.conv_dgrad(d, conv.w_op(), inp.shape, 1, pad)
             if k < 3:
-                O.act_bwd_(d, inp, O.ACT_RELU)       # inp is the ReLU output of the previous conv
+                O.act_bwd_(d, inp, O.ACT_RELU | O.rnd())       # inp is the ReLU output of the previous conv
         encoder_backward(self.encoder, rec["enc"], [None, None, None, None, d])
 
 

@@ -12,6 +12,7 @@ from . import lib as L
 PAD_ZERO, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_DISP = 0, 1, 2, 3
 BN_SLOTS = 16      # SCSFM_BN_SLOTS: replicas of the fused BatchNorm sums
+ROUND_TF32 = 0x100  # SCSFM_ROUND_TF32: store the result rounded to TF32 (operand of a tensor-core conv)
 
 # "fp32": exact CUDA-core kernels everywhere (parity mode).  "tf32": tcgen05 tensor-core kernels on the
 # layers they support (same arithmetic class as the reference's cuDNN TF32 default on GPU).
@@ -38,6 +39,7 @@ def _lib():
                      "scsfm_conv2d_fwd_tc", "scsfm_conv2d_dgrad_tc", "scsfm_conv2d_wgrad_tc"):
             if hasattr(lib, name):
                 getattr(lib, name).argtypes = [CP, P]
+        lib.scsfm_round_tf32.argtypes = [P, P, LL, P]
         if hasattr(lib, "scsfm_weight_flip"):
             lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
@@ -55,6 +57,15 @@ def _lib():
         lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P]
         _bound = True
     return lib
+
+
+def rnd():
+    """Flag to OR into act / relu arguments of kernels whose output feeds a tensor-core convolution."""
+    return ROUND_TF32 if CONFIG["conv_mode"] == "tf32" else 0
+
+
+def round_tf32(src, dst):
+    L.launch(_lib().scsfm_round_tf32, "scsfm_round_tf32", "weight_round", 1, 8.0 * src.numel(), L.ptr(src), L.ptr(dst), src.numel(), L.stream())
 
 
 def empty(shape, like):
@@ -193,7 +204,7 @@ def bn_apply(y, saved, residual, relu, groups=1):
     z = torch.empty_like(y)
     rows = y.numel() // y.shape[-1]
     L.launch(_lib().scsfm_bn_apply, "scsfm_bn_apply", "bn_apply", 1, (12.0 if residual is not None else 8.0) * y.numel(), L.ptr(y), L.ptr(saved), L.ptr(residual), L.ptr(z), rows, y.shape[-1], groups,
-                                  1 if relu else 0, L.stream())
+                                  int(relu), L.stream())
     return z
 
 
@@ -205,7 +216,7 @@ def bn_backward(dz, z, y, saved, dgamma, dbeta, relu, want_dres, groups=1):
     work = torch.empty(groups * C * 2, device=y.device, dtype=torch.float64)
     dres = dz if want_dres else None
     L.launch(_lib().scsfm_bn_backward, "scsfm_bn_backward", "bn_bwd", 4, 28.0 * y.numel(), L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(saved), None, L.ptr(dy), L.ptr(dres), L.ptr(dgamma),
-                                     L.ptr(dbeta), rows, C, groups, 1 if relu else 0, L.ptr(work), L.stream())
+                                     L.ptr(dbeta), rows, C, groups, int(relu), L.ptr(work), L.stream())
     return dy, dres
 
 

@@ -318,6 +318,9 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
     xc = x.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
     wc = w.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
     bc = b.detach().float().to(DEV) if bias else None
+    # the tensor-core kernels expect operands already rounded to TF32 by their producers (SCSFM_ROUND_TF32)
+    for tns in (xc, wc):
+        O.round_tf32(tns, tns)
     old = O.CONFIG["conv_mode"]
     O.CONFIG["conv_mode"] = "tf32"
     try:
@@ -329,6 +332,7 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
         np.testing.assert_allclose(s[:, 0], yc.double().sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
         np.testing.assert_allclose(s[:, 1], (yc.double() ** 2).sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
         dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+        O.round_tf32(dc, dc)
         if hasattr(L.load(), "scsfm_conv2d_wgrad_tc"):
             assert O._use_tc("wgrad", Cin, Cout, k, stride)
             dw = torch.zeros_like(wc)
@@ -336,7 +340,7 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
             O.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
             assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 1e-3
             if bias:
-                assert rel_l2(db, b.grad) < 1e-5
+                assert rel_l2(db, b.grad) < 1e-3     # dout was rounded to TF32 above
         if stride == 1:
             assert O._use_tc("dgrad", Cin, Cout, k, stride)
             O.invalidate_weight_cache()
@@ -378,8 +382,20 @@ def test_disp_net_tf32_mode_vs_oracle(golden_nets):
         sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(ro)).backward()
         grads = {k: p.grad for k, p in net.named_parameters()}
         errs = sorted(rel_l2(grads[k], p.grad) for k, p in ref.named_parameters() if p.grad is not None)
-        print("tf32 mode: per-parameter gradient rel-L2 vs fp64 oracle: median %.2e, worst %.2e" % (errs[len(errs) // 2], errs[-1]))
-        assert errs[len(errs) // 2] < 2e-2 and errs[-1] < 0.5
+        # yardstick: the same network in stock PyTorch on this GPU with cuDNN's TF32 convolutions (the reference's own
+        # default arithmetic on a GPU), against the same fp64 oracle
+        torch.backends.cudnn.allow_tf32 = True
+        stock = N.DispResNet(18).to(DEV)
+        stock.load_state_dict({k: v.to(DEV) for k, v in det_weights(stock.state_dict()).items()})
+        stock.train()
+        so = stock(img1.to(DEV))
+        sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(so)).backward()
+        sg = {k: p.grad for k, p in stock.named_parameters()}
+        errs_stock = sorted(rel_l2(sg[k], p.grad) for k, p in ref.named_parameters() if p.grad is not None)
+        med, med_stock = errs[len(errs) // 2], errs_stock[len(errs_stock) // 2]
+        print("tf32 mode: per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e | stock PyTorch/cuDNN TF32: median %.2e worst %.2e"
+              % (med, errs[-1], med_stock, errs_stock[-1]))
+        assert med < 3 * med_stock + 1e-3 and errs[-1] < 3 * errs_stock[-1] + 1e-2
     finally:
         O.CONFIG["conv_mode"] = old
         O.invalidate_weight_cache()
