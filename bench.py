@@ -340,7 +340,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--conv-mode", choices=["fp32", "tf32"], default="fp32")
+    ap.add_argument("--conv-mode", choices=["fp32", "tf32"], default="tf32",
+                    help="tf32 = tcgen05 tensor-core convolutions (the reference's own cuDNN default arithmetic on a GPU); fp32 = exact CUDA-core parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
