@@ -170,12 +170,15 @@ int scsfm_conv2d_dgrad_simt(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
 
 /* tcgen05 (kind::tf32, fp32 accumulation in TMEM) implicit-GEMM convolution; needs Cin % 4 == 0.
- * dgrad_tc: stride 1 only; p->w must hold the flipped/transposed weights [Cin,kh,kw,Cout] produced by
+ * dgrad_tc: stride 1 or 2; p->w must hold the flipped/transposed weights [Cin,kh,kw,Cout] produced by
  * scsfm_weight_flip (the data gradient is the forward kernel run on dout). */
 int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream);
 int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
+/* stride-2 data gradient: four parity-class weight sets back to back (Cin*kh*kw*Cout floats in total); p->w of
+ * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */
+int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream);
 
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
 int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);

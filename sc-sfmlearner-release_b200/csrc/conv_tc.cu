@@ -49,9 +49,19 @@ __device__ __forceinline__ float tc_act(float v, int act) {
     }
 }
 
+// Geometry of one (sub-)convolution as the kernel sees it.  A plain convolution uses the identity output map; a
+// stride-2 data gradient is run as four parity-class stride-1 sub-convolutions (output pixels 2h+py, 2w+px) whose
+// taps are the kernel rows/columns of matching parity -- no multiplications by inserted zeros.
+struct TcView {
+    int kh, kw;            // tap grid
+    int oy0, ox0;          // input row = ho * in_stride + oy0 + dy
+    int in_stride;
+    int out_sy, out_oy, out_sx, out_ox, out_H, out_W;   // output pixel (ho, wo) -> (ho*out_sy + out_oy, wo*out_sx + out_ox)
+};
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS)
-conv_fwd_tc_kernel(ScsfmConv p) {
+conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -64,7 +74,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.B * p.Ho * p.Wo, N = p.Cout, K = p.kh * p.kw * p.Cin;
+    const int M = p.B * p.Ho * p.Wo, N = p.Cout, K = v.kh * v.kw * p.Cin;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
     const int KB = (K + TBK - 1) / TBK;
 
@@ -94,8 +104,8 @@ conv_fwd_tc_kernel(ScsfmConv p) {
             const int m = m0 + r0 + 16 * i;
             if (m < M) {
                 const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
-                hi0[i] = ho * p.stride - p.pad;
-                wi0[i] = wo * p.stride - p.pad;
+                hi0[i] = ho * v.in_stride + v.oy0;
+                wi0[i] = wo * v.in_stride + v.ox0;
                 base[i] = p.in + (size_t)b * p.Hi * p.Wi * p.Cin;
             } else {
                 hi0[i] = -(1 << 28);          // always out of range -> zero rows
@@ -105,7 +115,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
         }
         int kc = 4 * c;
         int tap = kc / p.Cin, ch = kc - tap * p.Cin;
-        int dy = tap / p.kw, dx = tap - dy * p.kw;
+        int dy = tap / v.kw, dx = tap - dy * v.kw;
         const bool reflect = p.pad_mode == PADMODE_REFLECT;
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES;
@@ -146,7 +156,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
             ch += TBK;
             while (ch >= p.Cin) {
                 ch -= p.Cin;
-                if (++dx == p.kw) { dx = 0; ++dy; }
+                if (++dx == v.kw) { dx = 0; ++dy; }
             }
         }
 
@@ -155,6 +165,11 @@ conv_fwd_tc_kernel(ScsfmConv p) {
         tc::fence_after_thread_sync();
         const int m = m0 + warp * 32 + lane;
         const bool row_ok = m < M;
+        size_t out_row = (size_t)m;          // row of the output / addend tensors
+        if (row_ok && (v.out_sy != 1 || v.out_sx != 1)) {
+            const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
+            out_row = ((size_t)b * v.out_H + (ho * v.out_sy + v.out_oy)) * v.out_W + (wo * v.out_sx + v.out_ox);
+        }
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
         constexpr int CW = BN < 32 ? BN : 32;
 #pragma unroll 1
@@ -171,7 +186,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
                 float x = __uint_as_float(r[j]);
                 if (row_ok && n < N) {
                     if (p.bias) x += __ldg(p.bias + n);
-                    if (p.addend) x += __ldg(p.addend + (size_t)m * N + n);
+                    if (p.addend) x += __ldg(p.addend + out_row * N + n);
                     x = tc_act(x, p.act);
                     if (p.act & ROUND_TF32) x = tf32_round(x);
                 } else {
@@ -180,7 +195,7 @@ conv_fwd_tc_kernel(ScsfmConv p) {
                 v[j] = x;
             }
             if (row_ok) {
-                float* o = p.out + (size_t)m * N + n0 + cc * CW;
+                float* o = p.out + out_row * N + n0 + cc * CW;
                 if ((N & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < CW; j += 4)
@@ -259,14 +274,20 @@ conv_fwd_tc_kernel(ScsfmConv p) {
     if (warp == 4) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// w [Co][T][Ci] -> wt [Ci][T][Co] with the taps reversed: the weights of the transposed (data-gradient) conv
-__global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int T, int Ci, float* __restrict__ wt) {
-    const long long total = (long long)Co * T * Ci;
+// w [Co][kh][kw][Ci] -> wt [Ci][jh][jw][Co] with wt[c][jy][jx][o] = w[o][dy_max - step*jy][dx_max - step*jx][c]:
+// the (TF32-rounded) weights of the transposed conv.  step 1, d*_max = k-1: the full flipped kernel (stride-1 dgrad);
+// step 2: the taps of one output-parity class of a stride-2 dgrad.
+__global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int kh, int kw, int Ci, int jh, int jw, int dy_max,
+                                   int dx_max, int step, float* __restrict__ wt) {
+    const long long total = (long long)Co * jh * jw * Ci;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int o = (int)(i % Co);
-        const long long t2 = i / Co;
-        const int tap = (int)(t2 % T), c = (int)(t2 / T);
-        wt[i] = tf32_round(__ldg(w + ((size_t)o * T + (T - 1 - tap)) * Ci + c));   // operand of the tensor-core dgrad
+        long long t2 = i / Co;
+        const int jx = (int)(t2 % jw); t2 /= jw;
+        const int jy = (int)(t2 % jh);
+        const int c = (int)(t2 / jh);
+        const int dy = dy_max - step * jy, dx = dx_max - step * jx;
+        wt[i] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
     }
 }
 
@@ -473,8 +494,12 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     return SCSFM_OK;
 }
 
+static TcView plain_view(const ScsfmConv& p) {
+    return TcView{p.kh, p.kw, -p.pad, -p.pad, p.stride, 1, 0, 1, 0, p.Ho, p.Wo};
+}
+
 template <int BN>
-static int launch_fwd_tc(const ScsfmConv& p, cudaStream_t st) {
+static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -483,7 +508,7 @@ static int launch_fwd_tc(const ScsfmConv& p, cudaStream_t st) {
     }
     const int M = p.B * p.Ho * p.Wo;
     dim3 grid((M + TBM - 1) / TBM, (p.Cout + BN - 1) / BN);
-    conv_fwd_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p);
+    conv_fwd_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p, v);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -492,15 +517,15 @@ static int launch_fwd_tc(const ScsfmConv& p, cudaStream_t st) {
 
 using namespace scsfm;
 
-static int tc_dispatch(const ScsfmConv& p, cudaStream_t st) {
+static int tc_dispatch(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     const int N = p.Cout;
-    if (N <= 16) return launch_fwd_tc<16>(p, st);
-    if (N <= 32 || N % 64 != 0) return launch_fwd_tc<32>(p, st);
-    if (N <= 64 || N % 128 != 0) return launch_fwd_tc<64>(p, st);
+    if (N <= 16) return launch_fwd_tc<16>(p, v, st);
+    if (N <= 32 || N % 64 != 0) return launch_fwd_tc<32>(p, v, st);
+    if (N <= 64 || N % 128 != 0) return launch_fwd_tc<64>(p, v, st);
     // prefer more CTAs when the M extent is small (deep layers at 8x26 / 16x52)
     const int M = p.B * p.Ho * p.Wo;
-    if (((M + TBM - 1) / TBM) * (N / 128) < 148) return launch_fwd_tc<64>(p, st);
-    return launch_fwd_tc<128>(p, st);
+    if (((M + TBM - 1) / TBM) * (N / 128) < 148) return launch_fwd_tc<64>(p, v, st);
+    return launch_fwd_tc<128>(p, v, st);
 }
 
 static int check_tc(const ScsfmConv* p, const char* who) {
@@ -520,7 +545,7 @@ static int check_tc(const ScsfmConv* p, const char* who) {
 
 extern "C" int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream) {
     if (int rc = check_tc(p, "conv2d_fwd_tc")) return rc;
-    return tc_dispatch(*p, (cudaStream_t)stream);
+    return tc_dispatch(*p, plain_view(*p), (cudaStream_t)stream);
 }
 
 extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream) {
@@ -528,8 +553,31 @@ extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int C
     const long long total = (long long)Cout * kh * kw * Cin;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh * kw, Cin, wt);
+    weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, kh, kw, kh - 1, kw - 1, 1, wt);
     SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+// Stride-2 data gradient: wt4 receives the four parity-class weight sets back to back (class order (py,px) =
+// (0,0),(0,1),(1,0),(1,1)); total size = Cin*kh*kw*Cout floats, the same as the full flipped kernel.
+extern "C" int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream) {
+    SCSFM_CHECK_ARG(w && wt4 && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && pad >= 0, "weight_flip_s2: bad arguments");
+    size_t off = 0;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            int dy_max = kh - 1, dx_max = kw - 1;
+            while (dy_max >= 0 && ((py + pad - dy_max) & 1)) --dy_max;
+            while (dx_max >= 0 && ((px + pad - dx_max) & 1)) --dx_max;
+            const int jh = dy_max < 0 ? 0 : dy_max / 2 + 1, jw = dx_max < 0 ? 0 : dx_max / 2 + 1;
+            const long long total = (long long)Cout * jh * jw * Cin;
+            if (total > 0) {
+                int grid = (int)((total + 255) / 256);
+                if (grid > 148 * 16) grid = 148 * 16;
+                weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, 2, wt4 + off);
+                SCSFM_CHECK_LAUNCH();
+            }
+            off += (size_t)total;
+        }
     return SCSFM_OK;
 }
 
@@ -537,15 +585,60 @@ extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int C
 // scsfm_weight_flip) passed in p->w; p->din [B,Hi,Wi,Cin] (+ p->addend).
 extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG(p != nullptr && p->dout && p->w && p->din, "conv2d_dgrad_tc: null tensor");
-    SCSFM_CHECK_ARG(p->stride == 1, "conv2d_dgrad_tc: stride must be 1 (strided layers use the CUDA-core kernel)");
+    SCSFM_CHECK_ARG(p->stride == 1 || p->stride == 2, "conv2d_dgrad_tc: stride must be 1 or 2");
+    SCSFM_CHECK_ARG(p->kh == p->kw && p->kh - 1 - p->pad >= 0, "conv2d_dgrad_tc: square kernels only");
+    cudaStream_t st = (cudaStream_t)stream;
     ScsfmConv q = *p;
     q.in = p->dout; q.out = p->din; q.bias = nullptr; q.bn_sums = nullptr; q.act = SCSFM_ACT_NONE;
     q.Hi = p->Ho; q.Wi = p->Wo; q.Cin = p->Cout;
-    q.Ho = p->Hi; q.Wo = p->Wi; q.Cout = p->Cin;
-    q.pad = p->kh - 1 - p->pad; q.pad_mode = SCSFM_PADMODE_ZERO;
-    SCSFM_CHECK_ARG(p->kh == p->kw && q.pad >= 0, "conv2d_dgrad_tc: square kernels only");
-    if (int rc = check_tc(&q, "conv2d_dgrad_tc")) return rc;
-    return tc_dispatch(q, (cudaStream_t)stream);
+    q.Cout = p->Cin; q.pad_mode = SCSFM_PADMODE_ZERO;
+    if (p->stride == 1) {
+        q.Ho = p->Hi; q.Wo = p->Wi;
+        q.pad = p->kh - 1 - p->pad;
+        if (int rc = check_tc(&q, "conv2d_dgrad_tc")) return rc;
+        return tc_dispatch(q, plain_view(q), st);
+    }
+    // stride 2: p->w holds the four parity-class weight sets of scsfm_weight_flip_s2
+    SCSFM_CHECK_ARG((q.Cin & 3) == 0, "conv2d_dgrad_tc: needs Cout %% 4 == 0");
+    q.stride = 1;
+    size_t woff = 0;
+    bool covered_all = true;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            int dy_max = p->kh - 1, dx_max = p->kw - 1;
+            while (dy_max >= 0 && ((py + p->pad - dy_max) & 1)) --dy_max;
+            while (dx_max >= 0 && ((px + p->pad - dx_max) & 1)) --dx_max;
+            const int jh = dy_max < 0 ? 0 : dy_max / 2 + 1, jw = dx_max < 0 ? 0 : dx_max / 2 + 1;
+            const int Hs = (p->Hi - py + 1) / 2, Ws = (p->Wi - px + 1) / 2;
+            if (jh == 0 || jw == 0) { if (Hs > 0 && Ws > 0) covered_all = false; }
+            woff += (size_t)p->Cout * jh * jw * p->Cin;
+        }
+    if (!covered_all) {
+        // parity classes without taps (1x1 stride 2): their gradient is the addend alone (or zero)
+        const size_t bytes = (size_t)p->B * p->Hi * p->Wi * p->Cin * sizeof(float);
+        if (p->addend) SCSFM_CHECK_CUDA(cudaMemcpyAsync(p->din, p->addend, bytes, cudaMemcpyDeviceToDevice, st));
+        else SCSFM_CHECK_CUDA(cudaMemsetAsync(p->din, 0, bytes, st));
+    }
+    woff = 0;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            int dy_max = p->kh - 1, dx_max = p->kw - 1;
+            while (dy_max >= 0 && ((py + p->pad - dy_max) & 1)) --dy_max;
+            while (dx_max >= 0 && ((px + p->pad - dx_max) & 1)) --dx_max;
+            const int jh = dy_max < 0 ? 0 : dy_max / 2 + 1, jw = dx_max < 0 ? 0 : dx_max / 2 + 1;
+            const int Hs = (p->Hi - py + 1) / 2, Ws = (p->Wi - px + 1) / 2;
+            const size_t wcount = (size_t)p->Cout * jh * jw * p->Cin;
+            if (jh > 0 && jw > 0 && Hs > 0 && Ws > 0) {
+                ScsfmConv r = q;
+                r.w = p->w + woff;
+                r.Ho = Hs; r.Wo = Ws; r.kh = jh; r.kw = jw;
+                // input (dout) row of output hy and tap jy: hy + (py + pad - dy_max)/2 + jy
+                TcView v{jh, jw, (py + p->pad - dy_max) / 2, (px + p->pad - dx_max) / 2, 1, 2, py, 2, px, p->Hi, p->Wi};
+                if (int rc = tc_dispatch(r, v, st)) return rc;
+            }
+            woff += wcount;
+        }
+    return SCSFM_OK;
 }
 
 // dw [Cout,kh,kw,Cin] += dout^T x gather(in); dbias += column sums of dout.  Needs Cin % 4 == 0 and Cout % 4 == 0.

@@ -42,6 +42,7 @@ def _lib():
         lib.scsfm_round_tf32.argtypes = [P, P, LL, P]
         if hasattr(lib, "scsfm_weight_flip"):
             lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
+            lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
@@ -84,7 +85,7 @@ def tc_supported(kind, Cin, Cout, kh, stride):
     if kind == "fwd":
         return Cin % 4 == 0 and Cout >= 16
     if kind == "dgrad":                      # forward kernel on dout: its "Cin" is Cout, its "Cout" is Cin
-        return stride == 1 and Cout % 4 == 0 and Cin >= 16
+        return stride in (1, 2) and Cout % 4 == 0 and Cin >= 16
     if kind == "wgrad":
         return Cin % 4 == 0 and Cout % 4 == 0 and Cout >= 16
     return False
@@ -93,16 +94,20 @@ def tc_supported(kind, Cin, Cout, kh, stride):
 _flip_cache = {}
 
 
-def flipped_weights(w):
-    """[Cout,kh,kw,Cin] -> [Cin,kh,kw,Cout] with reversed taps (weights of the transposed conv), cached per
-    weight tensor until `invalidate_weight_cache()` is called (after every optimizer step)."""
-    key = (w.data_ptr(), tuple(w.shape))
+def flipped_weights(w, stride=1, pad=0):
+    """[Cout,kh,kw,Cin] -> weights of the transposed conv ([Cin,kh,kw,Cout], reversed taps; for stride 2 the four
+    parity-class tap subsets back to back), TF32-rounded, cached per weight tensor until `invalidate_weight_cache()`."""
+    key = (w.data_ptr(), tuple(w.shape), stride, pad)
     wt = _flip_cache.get(key)
     if wt is None:
         Cout, kh, kw, Cin = w.shape
         wt = empty((Cin, kh, kw, Cout), w)
-        L.launch(_lib().scsfm_weight_flip, "scsfm_weight_flip", "weight_flip", 1, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw, Cin,
-                 L.ptr(wt), L.stream())
+        if stride == 1:
+            L.launch(_lib().scsfm_weight_flip, "scsfm_weight_flip", "weight_flip", 1, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw, Cin,
+                     L.ptr(wt), L.stream())
+        else:
+            L.launch(_lib().scsfm_weight_flip_s2, "scsfm_weight_flip_s2", "weight_flip", 4, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw,
+                     Cin, pad, L.ptr(wt), L.stream())
         _flip_cache[key] = wt
     return wt
 
@@ -158,7 +163,7 @@ def conv_dgrad(dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=Fals
     tc = _use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
     _tag(d)
     if tc:
-        d.w = flipped_weights(w).data_ptr()
+        d.w = flipped_weights(w, stride, pad).data_ptr()
     fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
     L.launch(fn, "scsfm_conv2d_dgrad", "conv_dgrad_tc" if tc else "conv_dgrad_simt", 1, _flops(d), ctypes.byref(d), L.stream())
     return din

@@ -295,6 +295,8 @@ TC_CASES = [
     (2, 9, 13, 64, 256, 1, 1, 0, 0, 1, True),      # 1x1 expand + ReLU + bias
     (4, 64, 104, 64, 128, 3, 1, 1, 0, 0, False),   # large M -> 128-wide N tile (3-stage pipeline)
     (3, 64, 104, 128, 256, 1, 1, 0, 0, 0, False),  # 128-wide tile, two N tiles
+    (2, 25, 41, 64, 128, 3, 2, 1, 0, 0, False),    # stride 2 on odd sizes (parity classes of unequal size)
+    (2, 16, 52, 256, 512, 1, 2, 0, 0, 0, False),   # 1x1 stride 2: three parity classes have no taps
 ]
 
 
@@ -341,7 +343,7 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
             assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 1e-3
             if bias:
                 assert rel_l2(db, b.grad) < 1e-3     # dout was rounded to TF32 above
-        if stride == 1:
+        if stride in (1, 2):       # stride 2 runs as four parity-class sub-convolutions
             assert O._use_tc("dgrad", Cin, Cout, k, stride)
             O.invalidate_weight_cache()
             if pad_mode == 0:
