@@ -94,11 +94,14 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
 
     if (warp < 4) {
         // ------------------------------------------------------------------ producers
+        // Per k-block every thread fetches 8 A chunks + BN/16 W chunks (16 B each).  The loop is software-pipelined:
+        // the loads of k-block kb+1 are in flight while k-block kb is written to shared memory, all addressing is
+        // 32-bit offset arithmetic and out-of-image taps are handled without branches (clamped address + select).
         const int c = tid & 7;               // 16-byte chunk column inside the 128-byte row
         const int r0 = tid >> 3;             // rows r0 + 16*i
         const int cs = c ^ (r0 & 7);         // 128B swizzle: chunk ^= row % 8 (rows r0+16i share row % 8)
-        int hi0[8], wi0[8];
-        const float* base[8];
+        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        int hi0[8], wi0[8], rbase[8];        // first-tap input coordinates and the image offset of each row
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m0 + r0 + 16 * i;
@@ -106,51 +109,60 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
                 const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
                 hi0[i] = ho * v.in_stride + v.oy0;
                 wi0[i] = wo * v.in_stride + v.ox0;
-                base[i] = p.in + (size_t)b * p.Hi * p.Wi * p.Cin;
+                rbase[i] = b * p.Hi * p.Wi * p.Cin;
             } else {
                 hi0[i] = -(1 << 28);          // always out of range -> zero rows
                 wi0[i] = -(1 << 28);
-                base[i] = p.in;
+                rbase[i] = 0;
             }
         }
+        int wrow[BN / 16];                   // weight row offsets (n * K), -1 for rows beyond Cout
+#pragma unroll
+        for (int j = 0; j < BN / 16; ++j) {
+            const int n = n0 + r0 + 16 * j;
+            wrow[j] = n < N ? n * K : -1;
+        }
+        const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)(r0 * 128 + cs * 16);
+        const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)(r0 * 128 + cs * 16);
         int kc = 4 * c;
-        int tap = kc / p.Cin, ch = kc - tap * p.Cin;
-        int dy = tap / v.kw, dx = tap - dy * v.kw;
-        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        int dy, dx, ch;
+        {
+            const int tap = kc / p.Cin;
+            ch = kc - tap * p.Cin;
+            dy = tap / v.kw;
+            dx = tap - dy * v.kw;
+        }
+        // Asynchronous copies (cp.async / LDGSTS, 16 B, zero-fill for out-of-image taps): no register staging, so the
+        // loads of all pipeline stages are in flight at once; the stage's "full" mbarrier gets this thread's arrival
+        // when its copies have landed (cp.async.mbarrier.arrive.noinc).  The MMA thread issues fence.proxy.async after
+        // waiting on the barrier to order these generic-proxy writes before the tensor core's async-proxy reads.
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
-            tc::mbar_wait(bar_empty + s, ph ^ 1);
-            float4 va[8], vb[BN / 16];
+            if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
+            __syncwarp();
+            const uint32_t a_st = a_smem + (uint32_t)(s * A_STAGE_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES);
             const bool kok = kc < K;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 int hi = hi0[i] + dy, wi = wi0[i] + dx;
-                bool ok = kok;
+                bool ok;
                 if (reflect) {
-                    ok = ok && hi0[i] > -(1 << 27);
+                    ok = kok && hi0[i] > -(1 << 27);
                     hi = reflect_index(hi, p.Hi);
                     wi = reflect_index(wi, p.Wi);
                 } else {
-                    ok = ok && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                    ok = kok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
                 }
-                va[i] = ok ? __ldg(reinterpret_cast<const float4*>(base[i] + ((size_t)hi * p.Wi + wi) * p.Cin + ch))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int off = ok ? rbase[i] + (hi * p.Wi + wi) * p.Cin + ch : 0;
+                tc::cp_async_16(a_st + i * 2048, p.in + off, ok ? 16u : 0u);
             }
 #pragma unroll
             for (int j = 0; j < BN / 16; ++j) {
-                const int n = n0 + r0 + 16 * j;
-                vb[j] = (kok && n < N) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * K + kc))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool ok = kok && wrow[j] >= 0;
+                tc::cp_async_16(b_st + j * 2048, p.w + (ok ? wrow[j] + kc : 0), ok ? 16u : 0u);
             }
-            uint8_t* a_st = sA + s * A_STAGE_BYTES + cs * 16;
-            uint8_t* b_st = sB + s * Cfg::B_STAGE_BYTES + cs * 16;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a_st + (r0 + 16 * i) * 128) = va[i];
-#pragma unroll
-            for (int j = 0; j < BN / 16; ++j) *reinterpret_cast<float4*>(b_st + (r0 + 16 * j) * 128) = vb[j];
-            tc::fence_proxy_async();
-            tc::mbar_arrive(bar_full + s);
+            tc::cp_async_arrive_noinc(bar_full + s);
             // advance this thread's K index by one k-block
             kc += TBK;
             ch += TBK;
@@ -247,12 +259,13 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
     } else {
         // ------------------------------------------------------------------ MMA issuer (warp 4)
         constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 0, 0);
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            tc::mbar_wait(bar_full + s, ph);
-            tc::fence_after_thread_sync();
-            if (lane == 0) {
+        if (lane == 0) {                                 // one thread waits, issues and commits
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(bar_full + s, ph);
+                tc::fence_proxy_async();                 // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+                tc::fence_after_thread_sync();
                 const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
                 const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_STAGE_BYTES);
 #pragma unroll
@@ -263,9 +276,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
                 }
                 tc::mma_commit(bar_empty + s);           // frees the stage once these MMAs have read it
             }
-            __syncwarp();
+            tc::mma_commit(bar_acc);                     // accumulator complete
         }
-        if (lane == 0) tc::mma_commit(bar_acc);          // accumulator complete
         __syncwarp();
     }
 
@@ -347,18 +359,22 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
 
     if (warp < 4) {
         // ------------------------------------------------------------------ producers
-        // A: chunk c4 = tid % 32 (4 consecutive (tap,c) entries, fixed for the whole kernel), pixel rows tid/32 + 4*i
-        const int c4 = tid & 31, kr0 = tid >> 5;
+        // A: chunk c4 = tid % 32 (4 consecutive (tap,c) entries, fixed for the whole kernel) x 8 CONSECUTIVE pixels
+        // starting at 8 * (tid / 32): a warp reads 512 contiguous bytes per pixel, and stepping to the next pixel is
+        // one add (+ a rare row wrap).  Same software pipelining / branch-free predication as the forward kernel.
+        const int c4 = tid & 31, kq = tid >> 5;              // kq: which group of 8 pixels of the 32-pixel k-block
         const int mm = m0 + 4 * c4;
         const bool a_ok = mm < Mtot;
         int a_dy = 0, a_dx = 0, a_ch = 0;
         if (a_ok) {
             const int tap = mm / p.Cin;
             a_ch = mm - tap * p.Cin;
-            a_dy = tap / p.kw;
-            a_dx = tap - a_dy * p.kw;
+            a_dy = tap / p.kw - p.pad;
+            a_dx = tap - (tap / p.kw) * p.kw - p.pad;
         }
-        const int a_off = (c4 >> 3) * 512;                  // atom along M
+        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        // smem byte offsets of this thread's 8 A chunks inside a stage: pixel k = 8*kq + i -> group k/4, row k%4
+        const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)((c4 >> 3) * 512);
         const int a_chunk = c4 & 7;
         // B: BN/4 chunks per pixel row
         constexpr int BCH = BN / 4;                          // chunks per row: 8, 16 or 32
@@ -366,60 +382,47 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
         const int nn = n0 + 4 * b_c4;
         const bool b_ok = nn < N;
-        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)((b_c4 >> 3) * 512);
         // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
         int pb, pho, pwo;
         {
-            const int px = pix_begin + kr0;
+            const int px = pix_begin + 8 * kq;
             pb = px / (p.Ho * p.Wo);
             const int rem = px - pb * p.Ho * p.Wo;
             pho = rem / p.Wo;
             pwo = rem - pho * p.Wo;
         }
+        int pix0 = pix_begin;
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
-            tc::mbar_wait(bar_empty + s, ph ^ 1);
-            const int pix0 = pix_begin + kb * 32;
-            float4 va[8], vb[B_IT];
-            {
-                int b = pb, ho = pho, wo = pwo;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int px = pix0 + kr0 + 4 * i;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (a_ok && px < pix_end) {
-                        int hi = ho * p.stride + a_dy - p.pad, wi = wo * p.stride + a_dx - p.pad;
-                        bool ok = true;
-                        if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
-                        else ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
-                        if (ok) v = __ldg(reinterpret_cast<const float4*>(p.in + (((size_t)b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch));
-                    }
-                    va[i] = v;
-                    wo += 4;
-                    while (wo >= p.Wo) { wo -= p.Wo; if (++ho == p.Ho) { ho = 0; ++b; } }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < B_IT; ++i) {
-                const int px = pix0 + b_kr0 + (128 / BCH) * i;
-                vb[i] = (b_ok && px < pix_end) ? __ldg(reinterpret_cast<const float4*>(p.dout + (size_t)px * N + nn))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            uint8_t* a_st = sA + s * Cfg::A_BYTES + a_off;
-            uint8_t* b_st = sB + s * Cfg::B_BYTES + (b_c4 >> 3) * 512;
+            if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
+            __syncwarp();
+            const uint32_t a_st = a_smem + (uint32_t)(s * Cfg::A_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_BYTES);
+            int b = pb, ho = pho, wo = pwo;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int k = kr0 + 4 * i;                  // pixel row inside the block: group k/4, row k%4
-                *reinterpret_cast<float4*>(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16)) = va[i];
+                const int k = 8 * kq + i;                   // pixel row inside the block: group k/4, row k%4
+                const int px = pix0 + k;
+                int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
+                bool ok = a_ok && px < pix_end;
+                if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
+                else ok = ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                const int off = ok ? ((b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch : 0;
+                tc::cp_async_16(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16),
+                                p.in + off, ok ? 16u : 0u);
+                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } }
             }
 #pragma unroll
             for (int i = 0; i < B_IT; ++i) {
                 const int k = b_kr0 + (128 / BCH) * i;
-                *reinterpret_cast<float4*>(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16)) = vb[i];
+                const int px = pix0 + k;
+                const bool ok = b_ok && px < pix_end;
+                tc::cp_async_16(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
+                                p.dout + (ok ? (size_t)px * N + nn : 0), ok ? 16u : 0u);
             }
-            tc::fence_proxy_async();
-            tc::mbar_arrive(bar_full + s);
+            tc::cp_async_arrive_noinc(bar_full + s);
+            pix0 += 32;
             pwo += 32;
             while (pwo >= p.Wo) { pwo -= p.Wo; if (++pho == p.Ho) { pho = 0; ++pb; } }
         }
@@ -444,16 +447,17 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     } else {
         // ------------------------------------------------------------------ MMA issuer (warp 4)
         constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 1, 1);       // both operands MN-major
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            tc::mbar_wait(bar_full + s, ph);
-            tc::fence_after_thread_sync();
-            if (lane == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(bar_full + s, ph);
+                tc::fence_proxy_async();
+                tc::fence_after_thread_sync();
                 const uint32_t a_addr = tc::smem_u32(sA + s * Cfg::A_BYTES);
                 const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_BYTES);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {               // 4 pixel groups of 8 (UMMA K = 8 for tf32)
+                for (int j = 0; j < 4; ++j) {               // 4 x (2 pixel groups of 4): UMMA K = 8 for tf32
                     // LBO = 512 B between 32-channel atoms, SBO = distance between 4-pixel groups; 2 groups per MMA
                     const uint64_t da = tc::make_smem_desc(a_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
                     const uint64_t db = tc::make_smem_desc(b_addr + j * (2 * (BN / 32) * 512), 512, (BN / 32) * 512, tc::LAYOUT_SW128_BASE32B);
@@ -461,9 +465,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
                 }
                 tc::mma_commit(bar_empty + s);
             }
-            __syncwarp();
+            tc::mma_commit(bar_acc);
         }
-        if (lane == 0) tc::mma_commit(bar_acc);
         __syncwarp();
     }
     tc::fence_before_thread_sync();
