@@ -180,8 +180,18 @@ int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* 
  * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */
 int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream);
 
+/* Disparity heads (DispResNet.py:79-82,98): 3x3 reflection-padded conv with one output channel, exact fp32.
+ * in [B,H,W,C], w [9*C] (= [1,3,3,C]), out / dpre [B,H,W]; dw, dbias accumulated into. */
+int scsfm_head_conv_fwd(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int act, void* stream);
+int scsfm_head_conv_wgrad(const float* in, const float* dpre, float* dw, float* dbias, int B, int H, int W, int C, void* stream);
+
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
 int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);
+/* same with the channel count zero-padded to Cpad and values rounded to TF32 (7x7 stems on the tensor cores: 3 -> 4, 6 -> 8) */
+int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, void* stream);
+/* rows of C floats -> rows of Cpad floats (zero padded, TF32 rounded) and the inverse accumulation dst[r][c] += src[r][c] */
+int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, void* stream);
+int scsfm_unpad_add(const float* src, long long rows, int C, int Cpad, float* dst, void* stream);
 /* NHWC [B,H,W,C] -> NCHW */
 int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, void* stream);
 

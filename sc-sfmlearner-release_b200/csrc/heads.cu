@@ -1,0 +1,129 @@
+// Disparity heads: 3x3 reflection-padded convolution with ONE output channel + 10*sigmoid+0.01
+// (reference DispResNet.py:79-82,98), forward and weight gradient.  A GEMM with N = 1 wastes a tensor-core or SIMT
+// tile; these are HBM/L1-bound streaming kernels in exact fp32.
+#include "nn_common.cuh"
+
+namespace scsfm {
+
+constexpr int HT = 256;
+
+// out[p] = act(bias + sum_{tap,c} in[refl(p + tap)][c] * w[tap][c]);  one thread per pixel
+__global__ void __launch_bounds__(HT)
+head_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                int B, int H, int W, int C, int act) {
+    extern __shared__ float sw[];        // [9][C]
+    for (int i = threadIdx.x; i < 9 * C; i += HT) sw[i] = w[i];
+    __syncthreads();
+    const long long total = (long long)B * H * W;
+    const int C4 = C >> 2;
+    for (long long p = blockIdx.x * (long long)HT + threadIdx.x; p < total; p += (long long)gridDim.x * HT) {
+        const int x = (int)(p % W);
+        const long long t = p / W;
+        const int y = (int)(t % H), b = (int)(t / H);
+        float acc = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = reflect_index(y + dy, H);
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = reflect_index(x + dx, W);
+                const float4* src = reinterpret_cast<const float4*>(in + (((size_t)b * H + yy) * W + xx) * C);
+                const float4* ws = reinterpret_cast<const float4*>(sw + ((dy + 1) * 3 + dx + 1) * C);
+                for (int c = 0; c < C4; ++c) {
+                    const float4 a = __ldg(src + c), k = ws[c];
+                    acc = fmaf(a.x, k.x, acc); acc = fmaf(a.y, k.y, acc); acc = fmaf(a.z, k.z, acc); acc = fmaf(a.w, k.w, acc);
+                }
+            }
+        }
+        if ((act & 0xff) == ACT_DISP) acc = 10.0f * (1.0f / (1.0f + expf(-acc))) + 0.01f;
+        out[p] = acc;
+    }
+}
+
+// dw[tap][c] += sum_p dpre[p] * in[refl(p + tap)][c];  dbias += sum_p dpre[p]
+// thread = (pixel lane, 4-channel chunk): 9 float4 accumulators, grid-stride over pixels, block reduction, atomics.
+__global__ void __launch_bounds__(HT)
+head_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dpre, float* __restrict__ dw, float* __restrict__ dbias,
+                  int B, int H, int W, int C) {
+    const int C4 = C >> 2;
+    const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, lanes = HT / C4;
+    float4 acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gsum = 0.f;
+    const long long total = (long long)B * H * W;
+    if (pl < lanes) {
+        for (long long p = (long long)blockIdx.x * lanes + pl; p < total; p += (long long)gridDim.x * lanes) {
+            const float g = __ldg(dpre + p);
+            const int x = (int)(p % W);
+            const long long t2 = p / W;
+            const int y = (int)(t2 % H), b = (int)(t2 / H);
+            gsum += g;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = reflect_index(y + dy, H);
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = reflect_index(x + dx, W);
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + yy) * W + xx) * C) + c4);
+                    float4& r = acc[(dy + 1) * 3 + dx + 1];
+                    r.x = fmaf(g, a.x, r.x); r.y = fmaf(g, a.y, r.y); r.z = fmaf(g, a.z, r.z); r.w = fmaf(g, a.w, r.w);
+                }
+            }
+        }
+    }
+    // reduce over the pixel lanes of the block: one (tap, channel) column at a time through shared memory
+    __shared__ float4 red[HT];
+    for (int t = 0; t < 9; ++t) {
+        __syncthreads();
+        red[threadIdx.x] = pl < lanes ? acc[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        if (threadIdx.x < C4) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < lanes; ++l) {
+                const float4 v = red[l * C4 + threadIdx.x];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            float* d = dw + t * C + 4 * threadIdx.x;
+            red_add(d, s.x); red_add(d + 1, s.y); red_add(d + 2, s.z); red_add(d + 3, s.w);
+        }
+    }
+    if (dbias != nullptr) {
+        __syncthreads();
+        float* rf = reinterpret_cast<float*>(red);
+        rf[threadIdx.x] = (c4 == 0 && pl < lanes) ? gsum : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int i = 0; i < HT; ++i) s += rf[i];
+            red_add(dbias, s);
+        }
+    }
+}
+
+}  // namespace scsfm
+
+using namespace scsfm;
+
+extern "C" int scsfm_head_conv_fwd(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int act,
+                                   void* stream) {
+    SCSFM_CHECK_ARG(in && w && out && B > 0 && H >= 2 && W >= 2 && C >= 4 && (C & 3) == 0 && C <= 1024, "head_conv_fwd: bad arguments");
+    const long long total = (long long)B * H * W;
+    long long g = (total + HT - 1) / HT;
+    if (g > 148 * 16) g = 148 * 16;
+    head_fwd_kernel<<<(int)g, HT, 9 * C * sizeof(float), (cudaStream_t)stream>>>(in, w, bias, out, B, H, W, C, act);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_head_conv_wgrad(const float* in, const float* dpre, float* dw, float* dbias, int B, int H, int W, int C, void* stream) {
+    SCSFM_CHECK_ARG(in && dpre && dw && B > 0 && H >= 2 && W >= 2 && C >= 4 && (C & 3) == 0 && C <= 1024, "head_conv_wgrad: bad arguments");
+    const int lanes = HT / (C / 4);
+    const long long total = (long long)B * H * W;
+    long long g = (total + (long long)lanes * 64 - 1) / ((long long)lanes * 64);     // >= 64 pixels per lane
+    if (g > 148 * 4) g = 148 * 4;
+    if (g < 1) g = 1;
+    head_wgrad_kernel<<<(int)g, HT, 0, (cudaStream_t)stream>>>(in, dpre, dw, dbias, B, H, W, C);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}

@@ -32,6 +32,46 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __
     }
 }
 
+// [B,C,H,W] (x1 or x2 sources) -> NHWC with the channel count padded to Cpad (zeros): the 7x7 stems run on the tensor
+// cores with Cin 3 -> 4 / 6 -> 8
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int C, int HW, int Cpad,
+                                        float* __restrict__ out) {
+    const int Ct = C * (b ? 2 : 1);
+    const long long total = (long long)B * HW * Cpad;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % Cpad);
+        const long long px = i / Cpad;
+        const int bb = (int)(px / HW), p = (int)(px - (long long)bb * HW);
+        float v = 0.f;
+        if (c < Ct) {
+            const float* src = c < C ? a : b;
+            const int cc = c < C ? c : c - C;
+            v = tf32_round(__ldg(src + ((size_t)bb * C + cc) * HW + p));
+        }
+        out[i] = v;
+    }
+}
+
+// rows of C floats -> rows of Cpad floats (zero padded, TF32 rounded): stem weights [64*49][3] -> [64*49][4]
+__global__ void pad_channels_kernel(const float* __restrict__ src, long long rows, int C, int Cpad, float* __restrict__ dst) {
+    const long long total = rows * Cpad;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % Cpad);
+        const long long r = i / Cpad;
+        dst[i] = c < C ? tf32_round(__ldg(src + r * C + c)) : 0.f;
+    }
+}
+
+// dst[r][c] += src[r][c] for c < C (src rows have Cpad floats): padded stem weight gradient -> gradient arena
+__global__ void unpad_add_kernel(const float* __restrict__ src, long long rows, int C, int Cpad, float* __restrict__ dst) {
+    const long long total = rows * C;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        dst[i] += __ldg(src + r * Cpad + c);
+    }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int C, int HW, float* __restrict__ out) {
     const long long total = (long long)B * HW * C;
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -471,6 +511,27 @@ extern "C" int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, 
     SCSFM_CHECK_ARG(a && out && B > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
     const long long n = (long long)B * H * W * C * (b ? 2 : 1);
     nchw_to_nhwc_kernel<<<grid_for(n), NT, 0, ST>>>(a, b, B, C, H * W, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, void* stream) {
+    SCSFM_CHECK_ARG(a && out && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C * (b ? 2 : 1), "nchw_to_nhwc_pad: bad arguments");
+    nchw_to_nhwc_pad_kernel<<<grid_for((long long)B * H * W * Cpad), NT, 0, ST>>>(a, b, B, C, H * W, Cpad, out);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, void* stream) {
+    SCSFM_CHECK_ARG(src && dst && rows > 0 && C > 0 && Cpad >= C, "pad_channels: bad arguments");
+    pad_channels_kernel<<<grid_for(rows * Cpad), NT, 0, ST>>>(src, rows, C, Cpad, dst);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_unpad_add(const float* src, long long rows, int C, int Cpad, float* dst, void* stream) {
+    SCSFM_CHECK_ARG(src && dst && rows > 0 && C > 0 && Cpad >= C, "unpad_add: bad arguments");
+    unpad_add_kernel<<<grid_for(rows * C), NT, 0, ST>>>(src, rows, C, Cpad, dst);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

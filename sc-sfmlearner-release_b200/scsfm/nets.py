@@ -372,10 +372,23 @@ def block_backward(blk, r, d_out, extra_addend=None):
     return dx
 
 
-def encoder_forward(enc, x_nhwc, training, G=1):
+def encoder_forward(enc, imgs, training, G=1):
+    """imgs: tuple of one (DispResNet) or two (PoseResNet, channel-concatenated) NCHW image batches."""
     t = enc.encoder
-    rec = {"x": x_nhwc, "G": G}
-    rec["y0"], f0, rec["s0"] = _conv_bn(x_nhwc, t.conv1, t.bn1, 2, 3, training, True, None, G)
+    rec = {"G": G}
+    if O.CONFIG["conv_mode"] == "tf32":
+        # 7x7 stem on the tensor cores: input channels zero-padded 3 -> 4 / 6 -> 8 (K = 49 * Cpad), weights likewise
+        cpad = 4 * len(imgs)
+        x_nhwc = O.nchw_to_nhwc_pad(imgs[0], imgs[1] if len(imgs) > 1 else None, cpad)
+        w0 = O.pad_channels(t.conv1.w_khwc(), cpad)
+        C = w0.shape[0]
+        sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=x_nhwc.device, dtype=torch.float64) if training else None
+        rec["y0"] = O.conv_fwd(x_nhwc, w0, None, 2, 3, O.PAD_ZERO, O.ACT_NONE, sums, G)
+        f0, rec["s0"] = _bn_fwd(rec["y0"], sums, t.bn1, training, True, None, G)
+    else:
+        x_nhwc = O.nchw_to_nhwc(imgs[0], imgs[1] if len(imgs) > 1 else None)
+        rec["y0"], f0, rec["s0"] = _conv_bn(x_nhwc, t.conv1, t.bn1, 2, 3, training, True, None, G)
+    rec["x"] = x_nhwc
     rec["f0"] = f0
     pooled, rec["pool_idx"] = O.maxpool_fwd(f0)
     feats, blocks, x = [f0], [], pooled
@@ -413,7 +426,15 @@ def encoder_backward(enc, rec, d_feats):
     else:
         d_f0 = torch.empty_like(f0)
         O.maxpool_bwd(d, rec["pool_idx"], f0.shape, d_f0, False)
-    _conv_bn_bwd(d_f0, f0, rec["y0"], rec["s0"], rec["x"], t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
+    x = rec["x"]
+    if x.shape[-1] != t.conv1.weight.shape[1]:
+        # padded-channel stem (tf32 mode): weight gradient in the padded layout, then folded into the gradient arena
+        dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | O.rnd(), False, rec["G"])
+        dw = torch.zeros(t.conv1.weight.shape[0], t.conv1.k, t.conv1.k, x.shape[-1], device=x.device, dtype=torch.float32)
+        O.conv_wgrad(x, dy, dw, None, 2, 3, O.PAD_ZERO)
+        O.unpad_add_(ArenaNet.g(t.conv1.weight), dw)
+    else:
+        _conv_bn_bwd(d_f0, f0, rec["y0"], rec["s0"], x, t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -456,7 +477,7 @@ class DispResNet(ArenaNet):
         x = L.dev_f32(x, "DispResNet input")
         self.refresh_operand_weights()
         training = self.training
-        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(x), training, groups)
+        enc_rec, feats = encoder_forward(self.encoder, (x,), training, groups)
         dec = self.decoder
         rec = {"enc": enc_rec, "stages": {}}
         cur = feats[4]
@@ -471,7 +492,7 @@ class DispResNet(ArenaNet):
             cur = st["b"]
             if i < 4 and (training or i == 0):
                 dc = dec.disp(i)
-                disps[i] = O.conv_fwd(cur, dc.w_op(), dc.bias, 1, 1, O.PAD_REFLECT, O.ACT_DISP)
+                disps[i] = O.head_fwd(cur, dc.w_khwc(), dc.bias, O.ACT_DISP)
             rec["stages"][i] = st
         rec["disps"] = disps
         order = [0, 1, 2, 3] if training else [0]
@@ -496,7 +517,7 @@ class DispResNet(ArenaNet):
                 dc = dec.disp(i)
                 disp = rec["disps"][i]
                 dpre = O.act_bwd_(d_disp[i].reshape(disp.shape).clone(), disp, O.ACT_DISP)
-                O.conv_wgrad(b, dpre, g(dc.weight), dc.bias.grad, 1, 1, O.PAD_REFLECT)
+                O.head_wgrad(b, dpre, g(dc.weight), dc.bias.grad)
                 dpad = O.conv_dgrad(dpre, dc.w_op(), b.shape, 1, 1, None, padded_input=True)
                 if not have:
                     d_b = torch.empty_like(b)
@@ -556,7 +577,7 @@ class PoseResNet(ArenaNet):
         from . import lib as L
         img1, img2 = L.dev_f32(img1, "PoseResNet input"), L.dev_f32(img2, "PoseResNet input")
         self.refresh_operand_weights()
-        enc_rec, feats = encoder_forward(self.encoder, O.nchw_to_nhwc(img1, img2), self.training, groups)
+        enc_rec, feats = encoder_forward(self.encoder, (img1, img2), self.training, groups)
         n = self.decoder.net
         rec = {"enc": enc_rec, "f4": feats[4]}
         rec["s"] = O.conv_fwd(feats[4], n[0].w_op(), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU | O.rnd())

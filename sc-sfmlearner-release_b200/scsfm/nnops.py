@@ -45,6 +45,11 @@ def _lib():
             lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
+        lib.scsfm_head_conv_fwd.argtypes = [P, P, P, P, I, I, I, I, I, P]
+        lib.scsfm_head_conv_wgrad.argtypes = [P, P, P, P, I, I, I, I, P]
+        lib.scsfm_nchw_to_nhwc_pad.argtypes = [P, P, I, I, I, I, I, P, P]
+        lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, P]
+        lib.scsfm_unpad_add.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
         lib.scsfm_bn_apply.argtypes = [P, P, P, P, LL, I, I, I, P]
         lib.scsfm_bn_backward.argtypes = [P, P, P, P, P, P, P, P, P, LL, I, I, I, P, P]
@@ -183,11 +188,50 @@ def conv_wgrad(x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
              ctypes.byref(d), L.stream())
 
 
+def head_fwd(x, w, bias, act):
+    """Disparity head: 3x3 reflect conv to one channel (+ activation).  x [B,H,W,C], w [1,3,3,C] -> [B,H,W,1]."""
+    B, H, W, C = x.shape
+    out = empty((B, H, W, 1), x)
+    L.launch(_lib().scsfm_head_conv_fwd, "scsfm_head_conv_fwd", "head_fwd", 1, 4.0 * x.numel(), L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out),
+             B, H, W, C, act, L.stream())
+    return out
+
+
+def head_wgrad(x, dpre, dw, dbias):
+    B, H, W, C = x.shape
+    L.launch(_lib().scsfm_head_conv_wgrad, "scsfm_head_conv_wgrad", "head_wgrad", 1, 4.0 * x.numel(), L.ptr(x), L.ptr(dpre), L.ptr(dw),
+             L.ptr(dbias), B, H, W, C, L.stream())
+
+
 def nchw_to_nhwc(a, b=None):
     B, C, H, W = a.shape
     out = empty((B, H, W, C * (2 if b is not None else 1)), a)
     L.launch(_lib().scsfm_nchw_to_nhwc, "scsfm_nchw_to_nhwc", "layout", 1, 8.0 * out.numel(), L.ptr(a), L.ptr(b), B, C, H, W, L.ptr(out), L.stream())
     return out
+
+
+def nchw_to_nhwc_pad(a, b, Cpad):
+    B, C, H, W = a.shape
+    out = empty((B, H, W, Cpad), a)
+    L.launch(_lib().scsfm_nchw_to_nhwc_pad, "scsfm_nchw_to_nhwc_pad", "layout", 1, 8.0 * out.numel(), L.ptr(a), L.ptr(b), B, C, H, W, Cpad,
+             L.ptr(out), L.stream())
+    return out
+
+
+def pad_channels(w, Cpad):
+    """[..., C] -> [..., Cpad] zero padded, TF32 rounded (stem weights)."""
+    C = w.shape[-1]
+    out = empty(tuple(w.shape[:-1]) + (Cpad,), w)
+    L.launch(_lib().scsfm_pad_channels, "scsfm_pad_channels", "weight_round", 1, 8.0 * out.numel(), L.ptr(w), w.numel() // C, C, Cpad,
+             L.ptr(out), L.stream())
+    return out
+
+
+def unpad_add_(dst, src):
+    """dst[..., c] += src[..., c] for c < C."""
+    C, Cpad = dst.shape[-1], src.shape[-1]
+    L.launch(_lib().scsfm_unpad_add, "scsfm_unpad_add", "weight_round", 1, 12.0 * dst.numel(), L.ptr(src), dst.numel() // C, C, Cpad,
+             L.ptr(dst), L.stream())
 
 
 def nhwc_to_nchw(x):

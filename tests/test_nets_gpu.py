@@ -184,7 +184,7 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind):
         loss = (o * torch.arange(1, 7, dtype=o.dtype, device=DEV)).sum() * 100
         np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"{tag}_out"], rtol=1e-3, atol=2e-7)
     loss.backward()
-    np.testing.assert_allclose(float(loss.detach()), g[f"{tag}_loss"][0], rtol=2e-5)
+    np.testing.assert_allclose(float(loss.detach()), g[f"{tag}_loss"][0], rtol=2e-4)
     grads = {k: p.grad for k, p in net.named_parameters()}
     names = list(g[f"{tag}_grad_names"])
     norms = np.array([float(grads[k].double().norm()) for k in names])

@@ -40,15 +40,24 @@ def test_two_training_steps_match_the_oracle():
         # noise-determined wherever the gradient is ~0, so the two trajectories legitimately drift (~1e-3)
         np.testing.assert_allclose([float(v) for v in got], [float(v) for v in want], rtol=3e-4 if it == 0 else 5e-3, atol=1e-6)
         if it == 0:
-            worst = 0.0
+            # yardstick: the fp32 oracle's own gradient error against an fp64 run of the same step (kink pixels of the
+            # photometric / consistency terms differ between ANY two evaluations)
+            d64, p64 = N.DispResNet(18).double(), N.PoseResNet(18).double()
+            for net64 in (d64, p64):
+                net64.load_state_dict({k: v.double() for k, v in det_weights(net64.state_dict()).items()})
+                net64.train()
+            OS.train_step(d64, p64, OS.make_optimizer(d64, p64, lr=1e-4), tgt.double(), [r.double() for r in refs], K.double(),
+                          num_scales=1, with_ssim=1, with_mask=1, with_auto_mask=0)
+            g64 = {k: p.grad for k, p in d64.named_parameters() if p.grad is not None}
+            g32 = {k: p.grad for k, p in odisp.named_parameters() if p.grad is not None}
             for k, p in odisp.named_parameters():
                 if p.grad is None:
                     assert float(g_disp[k].abs().max()) == 0.0
-                    continue
-                e = rel_l2(g_disp[k], p.grad)
-                worst = max(worst, e)
-                assert e < 2e-2, (k, e)
-            print("worst DispResNet parameter-gradient rel-L2 vs fp32 oracle after a full step: %.2e" % worst)
+            mine = sorted(rel_l2(g_disp[k], g64[k]) for k in g64)
+            ref = sorted(rel_l2(g32[k], g64[k]) for k in g64)
+            print("DispResNet parameter-gradient rel-L2 vs fp64 oracle after a full step: CUDA median %.2e worst %.2e | fp32 CPU oracle "
+                  "median %.2e worst %.2e" % (mine[len(mine) // 2], mine[-1], ref[len(ref) // 2], ref[-1]))
+            assert mine[len(mine) // 2] < 3 * ref[len(ref) // 2] + 1e-4 and mine[-1] < 3 * ref[-1] + 1e-3
     # parameters after two Adam updates: elementwise bounded by 2 * lr (Adam's step bound), nearly all identical
     osd = odisp.state_dict()
     for k, v in disp.state_dict().items():
