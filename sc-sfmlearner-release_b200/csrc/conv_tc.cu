@@ -16,6 +16,8 @@
 // for reflection-padded layers it returns the gradient of the padded tensor (pad' = 2), folded afterwards.
 //
 // Replaces cuDNN implicit-GEMM fwd/dgrad for every layer with Cin % 4 == 0.
+#include <cuda.h>
+
 #include "nn_common.cuh"
 #include "tc_common.cuh"
 
@@ -23,12 +25,14 @@ namespace scsfm {
 
 constexpr int TBM = 128;            // tile rows (UMMA M)
 constexpr int TBK = 32;             // floats per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 160;       // wgrad kernel: 4 producer/epilogue warps + 1 MMA warp
+constexpr int FW_PWARPS = 8;          // forward/dgrad kernel: 8 producer/epilogue warps + 1 MMA warp
+constexpr int FW_THREADS = (FW_PWARPS + 1) * 32;
 constexpr int A_STAGE_BYTES = TBM * 128;
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;
+    static constexpr int STAGES = 3;
     static constexpr int B_STAGE_BYTES = BN * 128;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
@@ -60,8 +64,8 @@ struct TcView {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS)
-conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
+__global__ void __launch_bounds__(FW_THREADS)
+conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wmap) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -80,31 +84,33 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(bar_full + s, 128);
+            tc::mbar_init(bar_full + s, FW_PWARPS * 32 + 1);      // cp.async arrivals (activations) + 1 expect_tx arrival (weights, TMA)
             tc::mbar_init(bar_empty + s, 1);
         }
         tc::mbar_init(bar_acc, 1);
         tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&wmap);
     }
-    if (warp == 4) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < FW_PWARPS) {
         // ------------------------------------------------------------------ producers
-        // Per k-block every thread fetches 8 A chunks + BN/16 W chunks (16 B each).  The loop is software-pipelined:
+        // Per k-block every thread fetches 4 A chunks (16 B each); the BN x 32 weight slice is one TMA box.  The loop is software-pipelined:
         // the loads of k-block kb+1 are in flight while k-block kb is written to shared memory, all addressing is
         // 32-bit offset arithmetic and out-of-image taps are handled without branches (clamped address + select).
+        constexpr int ROWS = TBM / (FW_PWARPS * 4);    // A rows per thread (4): rows r0 + 32*i
         const int c = tid & 7;               // 16-byte chunk column inside the 128-byte row
-        const int r0 = tid >> 3;             // rows r0 + 16*i
-        const int cs = c ^ (r0 & 7);         // 128B swizzle: chunk ^= row % 8 (rows r0+16i share row % 8)
+        const int r0 = tid >> 3;             // 0..31
+        const int cs = c ^ (r0 & 7);         // 128B swizzle: chunk ^= row % 8 (rows r0+32i share row % 8)
         const bool reflect = p.pad_mode == PADMODE_REFLECT;
-        int hi0[8], wi0[8], rbase[8];        // first-tap input coordinates and the image offset of each row
+        int hi0[ROWS], wi0[ROWS], rbase[ROWS];   // first-tap input coordinates and the image offset of each row
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + r0 + 16 * i;
+        for (int i = 0; i < ROWS; ++i) {
+            const int m = m0 + r0 + 32 * i;
             if (m < M) {
                 const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
                 hi0[i] = ho * v.in_stride + v.oy0;
@@ -116,14 +122,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
                 rbase[i] = 0;
             }
         }
-        int wrow[BN / 16];                   // weight row offsets (n * K), -1 for rows beyond Cout
-#pragma unroll
-        for (int j = 0; j < BN / 16; ++j) {
-            const int n = n0 + r0 + 16 * j;
-            wrow[j] = n < N ? n * K : -1;
-        }
         const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)(r0 * 128 + cs * 16);
-        const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)(r0 * 128 + cs * 16);
+        const uint32_t b_smem = tc::smem_u32(sB);
         int kc = 4 * c;
         int dy, dx, ch;
         {
@@ -136,31 +136,45 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
         // loads of all pipeline stages are in flight at once; the stage's "full" mbarrier gets this thread's arrival
         // when its copies have landed (cp.async.mbarrier.arrive.noinc).  The MMA thread issues fence.proxy.async after
         // waiting on the barrier to order these generic-proxy writes before the tensor core's async-proxy reads.
+        // Row offsets / validity only change with the tap, i.e. every Cin/32 k-blocks: they are cached in between.
+        int aoff[ROWS];
+        uint32_t okm = 0;
+        int cur_dy = -1, cur_dx = -1;
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
             if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
             __syncwarp();
-            const uint32_t a_st = a_smem + (uint32_t)(s * A_STAGE_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES);
+            const uint32_t a_st = a_smem + (uint32_t)(s * A_STAGE_BYTES);
+            if (tid == 0) {
+                // weights: TMA box (32 K-columns x BN rows) straight into the 128B-swizzled stage; rows / columns beyond
+                // Cout / K are zero-filled by the hardware and still count towards the expected bytes
+                tc::mbar_arrive_expect_tx(bar_full + s, (uint32_t)Cfg::B_STAGE_BYTES);
+                tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), &wmap, kb * TBK, n0, bar_full + s);
+            }
+            if (dy != cur_dy || dx != cur_dx) {
+                cur_dy = dy; cur_dx = dx;
+                okm = 0;
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    int hi = hi0[i] + dy, wi = wi0[i] + dx;
+                    bool ok;
+                    if (reflect) {
+                        ok = hi0[i] > -(1 << 27);
+                        hi = reflect_index(hi, p.Hi);
+                        wi = reflect_index(wi, p.Wi);
+                    } else {
+                        ok = (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                    }
+                    aoff[i] = ok ? rbase[i] + (hi * p.Wi + wi) * p.Cin : 0;
+                    okm |= (ok ? 1u : 0u) << i;
+                }
+            }
             const bool kok = kc < K;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int hi = hi0[i] + dy, wi = wi0[i] + dx;
-                bool ok;
-                if (reflect) {
-                    ok = kok && hi0[i] > -(1 << 27);
-                    hi = reflect_index(hi, p.Hi);
-                    wi = reflect_index(wi, p.Wi);
-                } else {
-                    ok = kok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
-                }
-                const int off = ok ? rbase[i] + (hi * p.Wi + wi) * p.Cin + ch : 0;
-                tc::cp_async_16(a_st + i * 2048, p.in + off, ok ? 16u : 0u);
-            }
-#pragma unroll
-            for (int j = 0; j < BN / 16; ++j) {
-                const bool ok = kok && wrow[j] >= 0;
-                tc::cp_async_16(b_st + j * 2048, p.w + (ok ? wrow[j] + kc : 0), ok ? 16u : 0u);
+            for (int i = 0; i < ROWS; ++i) {
+                const bool ok = kok && ((okm >> i) & 1u);
+                tc::cp_async_16(a_st + i * 4096, p.in + (ok ? aoff[i] + ch : 0), ok ? 16u : 0u);
             }
             tc::cp_async_arrive_noinc(bar_full + s);
             // advance this thread's K index by one k-block
@@ -175,7 +189,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
         // ------------------------------------------------------------------ epilogue (same 4 warps)
         tc::mbar_wait(bar_acc, 0);
         tc::fence_after_thread_sync();
-        const int m = m0 + warp * 32 + lane;
+        const int quarter = warp & 3, half = warp >> 2;      // TMEM lane quarter / which half of the column chunks
+        const int m = m0 + quarter * 32 + lane;
         const bool row_ok = m < M;
         size_t out_row = (size_t)m;          // row of the output / addend tensors
         if (row_ok && (v.out_sy != 1 || v.out_sx != 1)) {
@@ -185,9 +200,9 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
         constexpr int CW = BN < 32 ? BN : 32;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / CW; ++cc) {
+        for (int cc = half; cc < BN / CW; cc += FW_PWARPS / 4) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * CW);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * CW);
             if (CW == 32) tc::tmem_ld32(taddr, r);
             else tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
@@ -229,7 +244,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
                     // 32 rows and flush the column sums whenever the group changes
                     const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
                     const int rows_per_group = (p.B / groups) * p.Ho * p.Wo;
-                    const int row_base = m0 + warp * 32;
+                    const int row_base = m0 + quarter * 32;
                     const int n = n0 + cc * CW + lane;
                     int g_cur = row_base / rows_per_group;
                     int next_edge = (g_cur + 1) * rows_per_group - row_base;      // first row index of the next group
@@ -283,7 +298,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v) {
 
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // w [Co][kh][kw][Ci] -> wt [Ci][jh][jw][Co] with wt[c][jy][jx][o] = w[o][dy_max - step*jy][dx_max - step*jx][c]:
@@ -510,8 +525,24 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
         configured = true;
     }
     const int M = p.B * p.Ho * p.Wo;
+    // TMA descriptor of the weight matrix [Cout rows][K columns] (K contiguous), box = 32 columns x BN rows, 128B swizzle
+    const int K = v.kh * v.kw * p.Cin;
+    CUtensorMap wmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)p.Cout};
+        const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BN};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = cuTensorMapEncodeTiled(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.w), gdim, gstride, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(weights %d x %d) failed with CUresult %d", p.Cout, K, (int)r);
+            return SCSFM_ERR_CUDA;
+        }
+    }
     dim3 grid((M + TBM - 1) / TBM, (p.Cout + BN - 1) / BN);
-    conv_fwd_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p, v);
+    conv_fwd_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, v, wmap);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
