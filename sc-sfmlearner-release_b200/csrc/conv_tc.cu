@@ -330,7 +330,7 @@ __global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int kh, 
 // ---------------------------------------------------------------------------------------------------------
 template <int BN>
 struct WgCfg {
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = 3;
     static constexpr int A_BYTES = 32 * TBM * 4;        // 32 pixels x 128 (tap,c)
     static constexpr int B_BYTES = 32 * BN * 4;         // 32 pixels x BN output channels
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -338,7 +338,7 @@ struct WgCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(FW_THREADS)
 conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     using Cfg = WgCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -360,24 +360,25 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(bar_full + s, 128);
+            tc::mbar_init(bar_full + s, FW_PWARPS * 32);
             tc::mbar_init(bar_empty + s, 1);
         }
         tc::mbar_init(bar_acc, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 4) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < FW_PWARPS) {
         // ------------------------------------------------------------------ producers
-        // A: chunk c4 = tid % 32 (4 consecutive (tap,c) entries, fixed for the whole kernel) x 8 CONSECUTIVE pixels
-        // starting at 8 * (tid / 32): a warp reads 512 contiguous bytes per pixel, and stepping to the next pixel is
-        // one add (+ a rare row wrap).  Same software pipelining / branch-free predication as the forward kernel.
-        const int c4 = tid & 31, kq = tid >> 5;              // kq: which group of 8 pixels of the 32-pixel k-block
+        // A: chunk c4 = tid % 32 (4 consecutive (tap,c) entries, fixed for the whole kernel) x PPT CONSECUTIVE pixels
+        // starting at PPT * (tid / 32): a warp reads 512 contiguous bytes per pixel, and stepping to the next pixel is
+        // one add (+ a rare row wrap).  cp.async with zero-fill, completion on the stage's mbarrier.
+        constexpr int PPT = 32 / FW_PWARPS;                   // pixels per thread per k-block (4)
+        const int c4 = tid & 31, kq = tid >> 5;              // kq: which group of PPT pixels of the 32-pixel k-block
         const int mm = m0 + 4 * c4;
         const bool a_ok = mm < Mtot;
         int a_dy = 0, a_dx = 0, a_ch = 0;
@@ -393,7 +394,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         const int a_chunk = c4 & 7;
         // B: BN/4 chunks per pixel row
         constexpr int BCH = BN / 4;                          // chunks per row: 8, 16 or 32
-        constexpr int B_IT = (32 * BCH) / 128;               // per-thread chunk loads: 2, 4, 8
+        constexpr int B_IT = (32 * BCH) / (FW_PWARPS * 32);  // per-thread chunk loads: 1, 2, 4
+        constexpr int B_STEP = (FW_PWARPS * 32) / BCH;       // pixel-row step between a thread's B chunks
         const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
         const int nn = n0 + 4 * b_c4;
         const bool b_ok = nn < N;
@@ -401,7 +403,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
         int pb, pho, pwo;
         {
-            const int px = pix_begin + 8 * kq;
+            const int px = pix_begin + PPT * kq;
             pb = px / (p.Ho * p.Wo);
             const int rem = px - pb * p.Ho * p.Wo;
             pho = rem / p.Wo;
@@ -416,8 +418,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
             const uint32_t a_st = a_smem + (uint32_t)(s * Cfg::A_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_BYTES);
             int b = pb, ho = pho, wo = pwo;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = 8 * kq + i;                   // pixel row inside the block: group k/4, row k%4
+            for (int i = 0; i < PPT; ++i) {
+                const int k = PPT * kq + i;                 // pixel row inside the block: group k/4, row k%4
                 const int px = pix0 + k;
                 int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
                 bool ok = a_ok && px < pix_end;
@@ -430,7 +432,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
             }
 #pragma unroll
             for (int i = 0; i < B_IT; ++i) {
-                const int k = b_kr0 + (128 / BCH) * i;
+                const int k = b_kr0 + B_STEP * i;
                 const int px = pix0 + k;
                 const bool ok = b_ok && px < pix_end;
                 tc::cp_async_16(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
@@ -445,11 +447,12 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         // ------------------------------------------------------------------ epilogue: dw[o][mm] += D[mm][o]
         tc::mbar_wait(bar_acc, 0);
         tc::fence_after_thread_sync();
-        const int row = m0 + warp * 32 + lane;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
+        for (int cc = half; cc < BN / 32; cc += FW_PWARPS / 4) {
             uint32_t r[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), r);
+            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
             tc::tmem_ld_wait();
             if (row < Mtot) {
 #pragma unroll
@@ -486,7 +489,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     }
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
@@ -501,13 +504,13 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     }
     const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * p.Ho * p.Wo;
     const int mt = (Mtot + TBM - 1) / TBM, nt = (p.Cout + BN - 1) / BN;
-    int splits = (148 * 2 + mt * nt - 1) / (mt * nt);
+    int splits = (148 * 3 + mt * nt - 1) / (mt * nt);          // 3 CTAs per SM fit
     const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
     dim3 grid(mt, nt, (npix + pps - 1) / pps);
-    conv_wgrad_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(p, pps);
+    conv_wgrad_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
