@@ -202,9 +202,12 @@ int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, 
 int scsfm_bn_prepare(const double* sums, int groups, int C, long long count_per_group, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                      int training, float* saved, void* stream);
-/* z = relu?(y*scale + shift + residual) */
-int scsfm_bn_apply(const float* y, const float* saved, const float* residual, float* z, long long rows, int C,
-                   int groups, int relu, void* stream);
+/* z = relu?(bn(y) + residual) with the statistics prepared INSIDE the kernel: training (sums != NULL) from the fused batch
+ * sums -- also writes `saved` and updates the running statistics like scsfm_bn_prepare; eval (sums == NULL) from the
+ * running statistics.  flags: bit 0 = ReLU, SCSFM_ROUND_TF32 = round the result. */
+int scsfm_bn_apply(const float* y, const double* sums, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* saved, const float* residual, float* z, long long rows,
+                   int C, int groups, int flags, void* stream);
 /* backward: given dz (gradient of z), z, y -> dy (overwrites `dy`), dres (= dz masked by relu; may be NULL or
  * alias dz), dgamma/dbeta accumulated into. `work` holds groups*C*2 doubles. */
 int scsfm_bn_backward(const float* dz, const float* z, const float* y, const float* saved, const float* gamma,

@@ -126,30 +126,97 @@ __global__ void bn_prepare_kernel(const double* __restrict__ sums, int G, int C,
     }
 }
 
-__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ saved, const float* __restrict__ res,
-                                float* __restrict__ z, long long rows, int C, long long rows_per_group, int relu) {
-    const int C4 = C >> 2;
-    const long long total = rows * C4;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const long long r = i / C4;
-        const int c = (int)(i - r * C4) * 4;
-        const int g = (int)(r / rows_per_group);
-        const float* sv = saved + ((size_t)g * C + c) * 4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
-        float o[4] = {v.x * sv[0] + sv[1], v.y * sv[4] + sv[5], v.z * sv[8] + sv[9], v.w * sv[12] + sv[13]};
+// z = relu?(y*scale + shift + residual), with scale/shift derived IN the kernel from the fused batch sums (training) or
+// taken from `saved` (eval).  Grid (row chunks, groups, channel slabs); a thread owns 4 consecutive channels and walks
+// rows, so there is no per-element index arithmetic: pure float4 streaming.  The first row-chunk CTA of every
+// (group, slab) writes saved[g][c] = {scale, shift, mean, invstd}; CTA (0,0,slab) also updates the running statistics
+// for all groups in call order.
+__global__ void __launch_bounds__(NT)
+bn_apply_kernel(const float* __restrict__ y, const double* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                int training, float* __restrict__ saved, const float* __restrict__ res, float* __restrict__ z,
+                long long rows_per_group, int C, int G, int flags, int rows_per_cta) {
+    const int g = blockIdx.y;
+    const int slab4 = min(C >> 2, NT);
+    const int col4 = blockIdx.z * slab4 + (threadIdx.x % slab4);
+    const int row_lanes = NT / slab4, rl = threadIdx.x / slab4;
+    const int c = col4 * 4;
+    // per-CTA statistics: one thread per channel of the slab (not one per row lane), shared through smem
+    __shared__ float s_sc[4 * NT], s_sh[4 * NT];
+    const double count = (double)rows_per_group;
+    const int slab_c0 = blockIdx.z * slab4 * 4, slab_cn = min(slab4 * 4, C - slab_c0);
+    for (int cc = threadIdx.x; cc < slab_cn; cc += NT) {
+        const int ch = slab_c0 + cc;
+        float mean, invstd;
+        if (training) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int slot = 0; slot < SCSFM_BN_SLOTS; ++slot) {
+                s1 += sums[(((size_t)slot * G + g) * C + ch) * 2];
+                s2 += sums[(((size_t)slot * G + g) * C + ch) * 2 + 1];
+            }
+            const double m = s1 / count;
+            double var = s2 / count - m * m;
+            if (var < 0) var = 0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + (double)eps));
+        } else {
+            mean = rmean[ch];
+            invstd = 1.0f / sqrtf(rvar[ch] + eps);
+        }
+        const float scale = gamma[ch] * invstd, shift = beta[ch] - mean * scale;
+        s_sc[cc] = scale;
+        s_sh[cc] = shift;
+        if (blockIdx.x == 0) {
+            float* o = saved + ((size_t)g * C + ch) * 4;
+            o[0] = scale; o[1] = shift; o[2] = mean; o[3] = invstd;
+        }
+    }
+    __syncthreads();
+    if (c >= C || rl >= row_lanes) return;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = s_sc[c - slab_c0 + j];
+        sh[j] = s_sh[c - slab_c0 + j];
+    }
+    if (training && blockIdx.x == 0 && blockIdx.y == 0 && rl == 0) {
+        // running statistics: one update per network call, in call order (nn.BatchNorm2d, momentum 0.1, unbiased variance)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float rm = rmean[c + j], rv = rvar[c + j];
+            for (int grp = 0; grp < G; ++grp) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int slot = 0; slot < SCSFM_BN_SLOTS; ++slot) {
+                    s1 += sums[(((size_t)slot * G + grp) * C + c + j) * 2];
+                    s2 += sums[(((size_t)slot * G + grp) * C + c + j) * 2 + 1];
+                }
+                const double m = s1 / count;
+                double var = s2 / count - m * m;
+                if (var < 0) var = 0;
+                const double unbiased = count > 1 ? var * count / (count - 1) : var;
+                rm = (1.f - momentum) * rm + momentum * (float)m;
+                rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+            }
+            rmean[c + j] = rm;
+            rvar[c + j] = rv;
+        }
+    }
+    const long long r0 = (long long)g * rows_per_group + (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min((long long)(g + 1) * rows_per_group, r0 + rows_per_cta);
+    const bool relu = flags & 1, rnd = flags & ROUND_TF32;
+    for (long long r = r0 + rl; r < r1; r += row_lanes) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
+        float o[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
         if (res) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + i);
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(res + r * C + c));
             o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
         }
-        if (relu & 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+        for (int j = 0; j < 4; ++j) {
+            if (relu) o[j] = fmaxf(o[j], 0.f);
+            if (rnd) o[j] = tf32_round(o[j]);
         }
-        if (relu & ROUND_TF32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = tf32_round(o[j]);
-        }
-        reinterpret_cast<float4*>(z)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(z + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -216,39 +283,50 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
     }
 }
 
-// pass 2: dy = gamma*invstd*(dz' - mean(dz') - xhat*mean(dz' xhat)); dres = dz'
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
-                                    const float* __restrict__ saved, const double* __restrict__ work, float* __restrict__ dy,
-                                    float* __restrict__ dres, long long rows, int C, long long rows_per_group, int relu) {
-    const int C4 = C >> 2;
-    const long long total = rows * C4;
+// pass 2: dy = gamma*invstd*(dz' - mean(dz') - xhat*mean(dz' xhat)); dres = dz'.  Same grid / thread layout as pass 1.
+__global__ void __launch_bounds__(NT)
+bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
+                    const float* __restrict__ saved, const double* __restrict__ work, float* __restrict__ dy,
+                    float* __restrict__ dres, long long rows_per_group, int C, int relu, int rows_per_cta) {
+    const int g = blockIdx.y;
+    const int slab4 = min(C >> 2, NT);
+    const int col4 = blockIdx.z * slab4 + (threadIdx.x % slab4);
+    const int row_lanes = NT / slab4, rl = threadIdx.x / slab4;
+    const int c = col4 * 4;
+    if (c >= C || rl >= row_lanes) return;
     const float inv_n = 1.0f / (float)rows_per_group;
-    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const long long r = i / C4;
-        const int c = (int)(i - r * C4) * 4;
-        const int g = (int)(r / rows_per_group);
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dz) + i);
-        const float4 y4 = __ldg(reinterpret_cast<const float4*>(y) + i);
+    float sc[4], mean[4], invstd[4], m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float* sv = saved + ((size_t)g * C + c + j) * 4;
+        sc[j] = sv[0]; mean[j] = sv[2]; invstd[j] = sv[3];
+        m1[j] = (float)work[((size_t)g * C + c + j) * 2] * inv_n;
+        m2[j] = (float)work[((size_t)g * C + c + j) * 2 + 1] * inv_n;
+    }
+    const long long r0 = (long long)g * rows_per_group + (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min((long long)(g + 1) * rows_per_group, r0 + rows_per_cta);
+    const bool gate = relu & 1, rnd = relu & ROUND_TF32;
+    for (long long r = r0 + rl; r < r1; r += row_lanes) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dz + r * C + c));
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
         float d[4] = {d4.x, d4.y, d4.z, d4.w};
         const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-        if (relu & 1) {
-            const float4 z4 = __ldg(reinterpret_cast<const float4*>(z) + i);
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (!(zz[j] > 0.f)) d[j] = 0.f;
+        if (gate) {
+            const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+            if (!(z4.x > 0.f)) d[0] = 0.f;
+            if (!(z4.y > 0.f)) d[1] = 0.f;
+            if (!(z4.z > 0.f)) d[2] = 0.f;
+            if (!(z4.w > 0.f)) d[3] = 0.f;
         }
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float* sv = saved + ((size_t)g * C + c + j) * 4;
-            const double* w = work + ((size_t)g * C + c + j) * 2;
-            const float xhat = (yy[j] - sv[2]) * sv[3];
-            o[j] = sv[0] * (d[j] - (float)w[0] * inv_n - xhat * (float)w[1] * inv_n);
-            if (relu & ROUND_TF32) o[j] = tf32_round(o[j]);
+            const float xhat = (yy[j] - mean[j]) * invstd[j];
+            o[j] = sc[j] * (d[j] - m1[j] - xhat * m2[j]);
+            if (rnd) o[j] = tf32_round(o[j]);
         }
-        if (dres) reinterpret_cast<float4*>(dres)[i] = make_float4(d[0], d[1], d[2], d[3]);
-        reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dres) *reinterpret_cast<float4*>(dres + r * C + c) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(dy + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -554,10 +632,30 @@ extern "C" int scsfm_bn_prepare(const double* sums, int groups, int C, long long
     return SCSFM_OK;
 }
 
-extern "C" int scsfm_bn_apply(const float* y, const float* saved, const float* residual, float* z, long long rows, int C,
-                              int groups, int relu, void* stream) {
-    SCSFM_CHECK_ARG(y && saved && z && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 && rows % groups == 0, "bn_apply: bad arguments");
-    bn_apply_kernel<<<grid_for(rows * (C / 4)), NT, 0, ST>>>(y, saved, residual, z, rows, C, rows / groups, relu);
+static void bn_grid(long long rpg, int C, int groups, dim3& grid, int& rpc) {
+    const int slab4 = (C / 4) < NT ? (C / 4) : NT;
+    const int slabs = (C / 4 + slab4 - 1) / slab4;
+    const int row_lanes = NT / slab4;
+    long long want = (148LL * 6 + (long long)groups * slabs - 1) / ((long long)groups * slabs);
+    long long max_chunks = (rpg + 4LL * row_lanes - 1) / (4LL * row_lanes);
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    rpc = (int)((rpg + want - 1) / want);
+    grid = dim3((unsigned)((rpg + rpc - 1) / rpc), groups, slabs);
+}
+
+// z = relu?(bn(y) + residual).  Training: statistics from the fused sums (also writes `saved`, updates running stats);
+// eval (sums == NULL): running statistics.
+extern "C" int scsfm_bn_apply(const float* y, const double* sums, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, float* saved, const float* residual, float* z,
+                              long long rows, int C, int groups, int flags, void* stream) {
+    SCSFM_CHECK_ARG(y && gamma && beta && running_mean && running_var && saved && z && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 &&
+                        rows % groups == 0, "bn_apply: bad arguments");
+    dim3 grid;
+    int rpc;
+    bn_grid(rows / groups, C, groups, grid, rpc);
+    bn_apply_kernel<<<grid, NT, 0, ST>>>(y, sums, gamma, beta, running_mean, running_var, momentum, eps, sums != nullptr, saved, residual, z,
+                                         rows / groups, C, groups, flags, rpc);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -582,7 +680,12 @@ extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y
     const int rpc = (int)((rpg + want - 1) / want);
     bn_bwd_reduce_kernel<<<dim3((unsigned)((rpg + rpc - 1) / rpc), groups, slabs), NT, 0, ST>>>(dz, z, y, saved, rpg, C, relu, rpc, work);
     SCSFM_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<<<grid_for(rows * (C / 4)), NT, 0, ST>>>(dz, z, y, saved, work, dy, dres, rows, C, rpg, relu);
+    {
+        dim3 grid2;
+        int rpc2;
+        bn_grid(rpg, C, groups, grid2, rpc2);
+        bn_bwd_apply_kernel<<<grid2, NT, 0, ST>>>(dz, z, y, saved, work, dy, dres, rpg, C, relu, rpc2);
+    }
     SCSFM_CHECK_LAUNCH();
     if (dgamma || dbeta) {
         bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST>>>(work, groups, C, dgamma, dbeta);

@@ -303,11 +303,10 @@ class _NetCall(torch.autograd.Function):
 def _bn_fwd(y, sums, bn, training, relu, residual, groups):
     """BatchNorm over `groups` independent sample groups (one per batched network call: statistics, and the
     running-stat updates, stay per call exactly as in train.py:427-442)."""
-    count = y.numel() // y.shape[-1] // groups
-    saved = O.bn_prepare(sums, groups, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, training)
     if training:
         bn.num_batches_tracked += groups
-    return O.bn_apply(y, saved, residual, (1 if relu else 0) | O.rnd(), groups), saved
+    return O.bn_apply(y, sums if training else None, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
+                      residual, (1 if relu else 0) | O.rnd(), groups)
 
 
 def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None, groups=1):

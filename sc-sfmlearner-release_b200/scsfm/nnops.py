@@ -51,7 +51,7 @@ def _lib():
         lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_unpad_add.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
-        lib.scsfm_bn_apply.argtypes = [P, P, P, P, LL, I, I, I, P]
+        lib.scsfm_bn_apply.argtypes = [P, P, P, P, P, P, F, F, P, P, P, LL, I, I, I, P]
         lib.scsfm_bn_backward.argtypes = [P, P, P, P, P, P, P, P, P, LL, I, I, I, P, P]
         lib.scsfm_maxpool_fwd.argtypes = [P, I, I, I, I, P, P, P]
         lib.scsfm_maxpool_bwd.argtypes = [P, P, I, I, I, I, P, I, P]
@@ -249,12 +249,17 @@ def bn_prepare(sums, groups, count, gamma, beta, rmean, rvar, momentum, eps, tra
     return saved
 
 
-def bn_apply(y, saved, residual, relu, groups=1):
+def bn_apply(y, sums, gamma, beta, rmean, rvar, momentum, eps, residual, flags, groups=1):
+    """z = relu?(bn(y) + residual); statistics from the fused sums (training) or the running stats (sums=None).
+    Returns (z, saved) with saved[g][c] = {scale, shift, mean, invstd} for the backward."""
     z = torch.empty_like(y)
-    rows = y.numel() // y.shape[-1]
-    L.launch(_lib().scsfm_bn_apply, "scsfm_bn_apply", "bn_apply", 1, (12.0 if residual is not None else 8.0) * y.numel(), L.ptr(y), L.ptr(saved), L.ptr(residual), L.ptr(z), rows, y.shape[-1], groups,
-                                  int(relu), L.stream())
-    return z
+    C = y.shape[-1]
+    saved = empty((groups, C, 4), y)
+    rows = y.numel() // C
+    L.launch(_lib().scsfm_bn_apply, "scsfm_bn_apply", "bn_apply", 1, (12.0 if residual is not None else 8.0) * y.numel(), L.ptr(y), L.ptr(sums),
+             L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar), momentum, eps, L.ptr(saved), L.ptr(residual), L.ptr(z), rows, C, groups,
+             int(flags), L.stream())
+    return z, saved
 
 
 def bn_backward(dz, z, y, saved, dgamma, dbeta, relu, want_dres, groups=1):
