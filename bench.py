@@ -165,13 +165,13 @@ def run_ours(args):
     graphed = world == 1 and not args.no_graph
     if graphed:
         trainer.capture(d_tgt, d_refs, d_K)
-    L.STATS["launches"] = 0
+    launches0 = L.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(lambda: trainer.step(d_tgt, d_refs, d_K), args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = trainer.launches_per_step * args.steps if graphed else L.STATS["launches"]
+    launches = trainer.launches_per_step * args.steps if graphed else (L.launch_count() - launches0)
 
     # ---- end to end: pinned host inputs copied in, loss read back, every step ----------------------
     result = torch.empty(4, dtype=torch.float32).pin_memory()

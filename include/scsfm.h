@@ -40,6 +40,9 @@ extern "C" {
 
 const char* scsfm_last_error(void);
 int scsfm_version(void);
+/* Number of CUDA kernels this library has launched so far in the process (every launch site counts itself):
+ * bench.py reports the difference over its timed region as "gpu_launches". */
+long long scsfm_launch_count(void);
 
 /* One pair-direction of compute_photo_and_geometry_loss (reference loss_functions.py:84-87):
  * warp `ref_*` into the view of `tgt_*`.  Depth maps may be coarser than the image by a power
@@ -172,9 +175,16 @@ int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
 /* tcgen05 (kind::tf32, fp32 accumulation in TMEM) implicit-GEMM convolution; needs Cin % 4 == 0.
  * dgrad_tc: stride 1 or 2; p->w must hold the flipped/transposed weights [Cin,kh,kw,Cout] produced by
  * scsfm_weight_flip (the data gradient is the forward kernel run on dout). */
+/* Stride-1 (sub-)convolutions with kh, kw <= 3 run the TMA halo-patch kernel (conv_tma.cu: one 4-D tiled TMA load
+ * per (channel chunk, dx) brings the input patch of a 2-D output tile, the kh vertical taps reuse it); reflection-
+ * padded layers run it zero-padded and recompute the border ring with the gather kernel.  Other shapes (stride-2
+ * forward, 7x7 stems) use the cp.async gather kernel. */
 int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream);
+/* test / experiment hook: enable = 0 routes every layer through the gather kernel; force_mt (1|2 stacked 128-pixel
+ * sub-tiles), force_bn (16|32|64|128), force_tw_log2 (3|4) override the tile heuristic, 0 = automatic */
+int scsfm_conv_tma_config(int enable, int force_mt, int force_bn, int force_tw_log2);
 int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
 /* stride-2 data gradient: four parity-class weight sets back to back (Cin*kh*kw*Cout floats in total); p->w of
  * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */

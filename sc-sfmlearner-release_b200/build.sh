@@ -15,5 +15,5 @@ for s in csrc/*.cu; do
   OBJS="$OBJS $o"
 done
 for p in $PIDS; do wait $p; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $OBJS -lcudart -lcuda
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $OBJS -lcudart
 echo "built $OUT"

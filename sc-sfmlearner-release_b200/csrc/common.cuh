@@ -28,7 +28,13 @@ void set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define SCSFM_CHECK_LAUNCH() SCSFM_CHECK_CUDA(cudaGetLastError())
+// every kernel launch site ends with this macro: it also feeds scsfm_launch_count() (bench.py's "gpu_launches")
+extern long long g_launch_count;
+#define SCSFM_CHECK_LAUNCH()                                   \
+    do {                                                       \
+        __atomic_add_fetch(&scsfm::g_launch_count, 1, __ATOMIC_RELAXED); \
+        SCSFM_CHECK_CUDA(cudaGetLastError());                  \
+    } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

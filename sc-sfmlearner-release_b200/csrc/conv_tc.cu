@@ -16,52 +16,9 @@
 // for reflection-padded layers it returns the gradient of the padded tensor (pad' = 2), folded afterwards.
 //
 // Replaces cuDNN implicit-GEMM fwd/dgrad for every layer with Cin % 4 == 0.
-#include <cuda.h>
-
-#include "nn_common.cuh"
-#include "tc_common.cuh"
+#include "conv_tc.cuh"
 
 namespace scsfm {
-
-constexpr int TBM = 128;            // tile rows (UMMA M)
-constexpr int TBK = 32;             // floats per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 160;       // wgrad kernel: 4 producer/epilogue warps + 1 MMA warp
-constexpr int FW_PWARPS = 8;          // forward/dgrad kernel: 8 producer/epilogue warps + 1 MMA warp
-constexpr int FW_THREADS = (FW_PWARPS + 1) * 32;
-constexpr int A_STAGE_BYTES = TBM * 128;
-
-template <int BN>
-struct TcCfg {
-    static constexpr int STAGES = 3;
-    static constexpr int B_STAGE_BYTES = BN * 128;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
-};
-
-// Operand precision: kind::tf32 TRUNCATES the low 13 mantissa bits of whatever fp32 pattern sits in shared memory
-// (measured: a systematic -7e-4 relative bias per dot product).  Converting with cvt.rna inside the loaders costs
-// ~50% of the loader-bound kernel time, so the operands are rounded ONCE where they are produced instead: every
-// kernel that writes a tensor later consumed by a convolution takes the SCSFM_ROUND_TF32 flag, and the weights are
-// rounded per optimizer step (scsfm_round_tf32).  The loaders below therefore copy bits unchanged.
-
-__device__ __forceinline__ float tc_act(float v, int act) {
-    switch (act & 0xff) {
-        case ACT_RELU: return fmaxf(v, 0.f);
-        case ACT_ELU: return v > 0.f ? v : expm1f(v);
-        case ACT_DISP: return 10.0f * (1.0f / (1.0f + expf(-v))) + 0.01f;
-        default: return v;
-    }
-}
-
-// Geometry of one (sub-)convolution as the kernel sees it.  A plain convolution uses the identity output map; a
-// stride-2 data gradient is run as four parity-class stride-1 sub-convolutions (output pixels 2h+py, 2w+px) whose
-// taps are the kernel rows/columns of matching parity -- no multiplications by inserted zeros.
-struct TcView {
-    int kh, kw;            // tap grid
-    int oy0, ox0;          // input row = ho * in_stride + oy0 + dy
-    int in_stride;
-    int out_sy, out_oy, out_sx, out_ox, out_H, out_W;   // output pixel (ho, wo) -> (ho*out_sy + out_oy, wo*out_sx + out_ox)
-};
 
 template <int BN>
 __global__ void __launch_bounds__(FW_THREADS)
@@ -78,7 +35,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.B * p.Ho * p.Wo, N = p.Cout, K = v.kh * v.kw * p.Cin;
+    const int rows_per_img = v.border ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo;
+    const int M = p.B * rows_per_img, N = p.Cout, K = v.kh * v.kw * p.Cin;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
     const int KB = (K + TBK - 1) / TBK;
 
@@ -112,7 +70,10 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         for (int i = 0; i < ROWS; ++i) {
             const int m = m0 + r0 + 32 * i;
             if (m < M) {
-                const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
+                const int b = m / rows_per_img, rem = m - b * rows_per_img;
+                int ho, wo;
+                if (v.border) border_pixel(rem, p.Ho, p.Wo, ho, wo);
+                else { ho = rem / p.Wo; wo = rem - ho * p.Wo; }
                 hi0[i] = ho * v.in_stride + v.oy0;
                 wi0[i] = wo * v.in_stride + v.ox0;
                 rbase[i] = b * p.Hi * p.Wi * p.Cin;
@@ -193,8 +154,11 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         const int m = m0 + quarter * 32 + lane;
         const bool row_ok = m < M;
         size_t out_row = (size_t)m;          // row of the output / addend tensors
-        if (row_ok && (v.out_sy != 1 || v.out_sx != 1)) {
-            const int b = m / (p.Ho * p.Wo), rem = m - b * p.Ho * p.Wo, ho = rem / p.Wo, wo = rem - ho * p.Wo;
+        if (row_ok && (v.out_sy != 1 || v.out_sx != 1 || v.border)) {
+            const int b = m / rows_per_img, rem = m - b * rows_per_img;
+            int ho, wo;
+            if (v.border) border_pixel(rem, p.Ho, p.Wo, ho, wo);
+            else { ho = rem / p.Wo; wo = rem - ho * p.Wo; }
             out_row = ((size_t)b * v.out_H + (ho * v.out_sy + v.out_oy)) * v.out_W + (wo * v.out_sx + v.out_ox);
         }
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
@@ -243,7 +207,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                     // a tile may straddle BatchNorm groups (network calls batched into one launch): walk the warp's
                     // 32 rows and flush the column sums whenever the group changes
                     const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
-                    const int rows_per_group = (p.B / groups) * p.Ho * p.Wo;
+                    const int rows_per_group = (p.B / groups) * rows_per_img;
                     const int row_base = m0 + quarter * 32;
                     const int n = n0 + cc * CW + lane;
                     int g_cur = row_base / rows_per_group;
@@ -492,6 +456,23 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t rank, void* gaddr, const cuuint64_t* gdim,
+                      const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+    using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Fn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || sym == nullptr ||
+            qres != cudaDriverEntryPointSuccess)
+            return CUDA_ERROR_NOT_FOUND;
+        fn = reinterpret_cast<Fn>(sym);
+    }
+    return fn(map, dtype, rank, gaddr, gdim, gstride, box, estr, il, sw, l2, oob);
+}
+
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
 
 template <int BN>
@@ -527,7 +508,7 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
         SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
-    const int M = p.B * p.Ho * p.Wo;
+    const int M = p.B * (v.border ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     // TMA descriptor of the weight matrix [Cout rows][K columns] (K contiguous), box = 32 columns x BN rows, 128B swizzle
     const int K = v.kh * v.kw * p.Cin;
     CUtensorMap wmap;
@@ -536,7 +517,7 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
         const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
         const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BN};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = cuTensorMapEncodeTiled(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.w), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.w), gdim, gstride, box, estr,
                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -554,15 +535,31 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
 
 using namespace scsfm;
 
-static int tc_dispatch(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
+// cp.async gather kernel: any stride / padding mode / border-only rows
+static int tc_dispatch_gather(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     const int N = p.Cout;
     if (N <= 16) return launch_fwd_tc<16>(p, v, st);
     if (N <= 32 || N % 64 != 0) return launch_fwd_tc<32>(p, v, st);
     if (N <= 64 || N % 128 != 0) return launch_fwd_tc<64>(p, v, st);
     // prefer more CTAs when the M extent is small (deep layers at 8x26 / 16x52)
-    const int M = p.B * p.Ho * p.Wo;
+    const int M = p.B * (v.border ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     if (((M + TBM - 1) / TBM) * (N / 128) < 148) return launch_fwd_tc<64>(p, v, st);
     return launch_fwd_tc<128>(p, v, st);
+}
+
+static int tc_dispatch(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
+    if (p.pad_mode == PADMODE_ZERO && conv_tma_eligible(p, v)) return launch_conv_tma(p, v, st);
+    if (p.pad_mode == PADMODE_REFLECT && p.bn_sums == nullptr && p.Ho >= 3 && p.Wo >= 3 && conv_tma_eligible(p, v)) {
+        // reflection padding only changes the outermost ring of output pixels: run the TMA kernel with zero padding
+        // (interior exact), then recompute the 2*(Ho+Wo)-4 border pixels per image with the reflecting gather kernel
+        ScsfmConv q = p;
+        q.pad_mode = PADMODE_ZERO;
+        if (int rc = launch_conv_tma(q, v, st)) return rc;
+        TcView bv = v;
+        bv.border = 1;
+        return tc_dispatch_gather(p, bv, st);
+    }
+    return tc_dispatch_gather(p, v, st);
 }
 
 static int check_tc(const ScsfmConv* p, const char* who) {

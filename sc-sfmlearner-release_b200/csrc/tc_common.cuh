@@ -58,6 +58,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tenso
                  ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+// 4-D tiled bulk tensor load (NHWC activations: coordinates c, x, y, b; out-of-range elements are zero-filled)
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tensor_map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tensor_map)) : "memory");
 }

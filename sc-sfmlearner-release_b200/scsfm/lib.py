@@ -48,6 +48,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.scsfm_last_error.restype = ctypes.c_char_p
     lib.scsfm_version.restype = ctypes.c_int
+    lib.scsfm_launch_count.restype = ctypes.c_longlong
     lib.scsfm_pairwise_stats_bytes.restype = ctypes.c_size_t
     lib.scsfm_pairwise_stats_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.scsfm_smooth_stats_bytes.restype = ctypes.c_size_t
@@ -90,7 +91,11 @@ def dev_f32(t, name):
 
 
 # ----- launch accounting / optional per-family CUDA-event profiling (used by bench.py) -------------
-STATS = {"launches": 0}
+def launch_count():
+    """Kernels launched by libscsfm so far in this process (counted at every launch site inside the library)."""
+    return int(load().scsfm_launch_count())
+
+
 PROF = {"enabled": False, "only": None, "events": []}
 
 
@@ -98,9 +103,9 @@ TAG = {"next": None}      # optional shape label attached to the next profiled l
 
 
 def launch(fn, what, family, n_kernels, work, *args):
-    """Call a C-ABI entry point; count its kernel launches; optionally bracket it with CUDA events on the
-    launching stream.  `work` = algorithmic FLOPs (convs) or bytes (HBM-bound ops) of the call."""
-    STATS["launches"] += n_kernels
+    """Call a C-ABI entry point; optionally bracket it with CUDA events on the launching stream.
+    `work` = algorithmic FLOPs (convs) or bytes (HBM-bound ops) of the call; `n_kernels` is documentation only
+    (the library counts its own launches: launch_count())."""
     if PROF["enabled"] and (PROF["only"] is None or family in PROF["only"]):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

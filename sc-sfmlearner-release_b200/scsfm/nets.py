@@ -229,6 +229,15 @@ class ArenaNet(nn.Module):
             off += _aligned(cnt)
         self._flat, self._flat_grad, self._views = flat, gflat, views
         self._hook = torch.zeros(1, device=dev, requires_grad=True)
+        # num_batches_tracked of all BatchNorm layers as views of one int64 tensor (one add per network call)
+        bns = [m for m in self.modules() if isinstance(m, BNParams)]
+        if bns:
+            nbt = torch.stack([m.num_batches_tracked.to(dev) for m in bns])
+            for i, m in enumerate(bns):
+                m.num_batches_tracked = nbt[i]
+            for m in self.modules():
+                if isinstance(m, ResnetEncoder):
+                    m._nbt = nbt
         # TF32-rounded mirror of the parameter arena (refreshed at the start of every network call in tf32 mode)
         self._flat_tf32 = torch.zeros_like(flat)
         off = 0
@@ -300,18 +309,47 @@ class _NetCall(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # encoder execution
 # ------------------------------------------------------------------------------------------------
+class _SumsPool:
+    """fp64 scratch for the fused BatchNorm sums of one network call: ONE fill per call instead of one torch.zeros per
+    layer.  Each layer's slice is consumed by bn_apply right after the convolution that accumulates into it, so the
+    pool is recycled by the next call.  It grows to the largest call seen (growth happens during the eager warm-up,
+    i.e. before any CUDA-graph capture)."""
+
+    def __init__(self):
+        self.buf, self.cursor, self.need = {}, 0, 0
+
+    def begin(self, device):
+        self.need = max(self.need, self.cursor)
+        buf = self.buf.get(device)
+        if buf is None or buf.numel() < self.need:
+            buf = self.buf[device] = torch.zeros(max(self.need, 1 << 16), device=device, dtype=torch.float64)
+        elif self.cursor:
+            buf[:self.cursor].zero_()
+        self.cursor = 0
+
+    def take(self, n, device):
+        n = (n + 31) // 32 * 32                      # 256-byte aligned slices
+        buf = self.buf.get(device)
+        start, self.cursor = self.cursor, self.cursor + n
+        if buf is None or self.cursor > buf.numel():
+            return torch.zeros(n, device=device, dtype=torch.float64)       # first (sizing) call only
+        return buf[start:start + n]
+
+
+_SUMS = _SumsPool()
+
+
 def _bn_fwd(y, sums, bn, training, relu, residual, groups):
     """BatchNorm over `groups` independent sample groups (one per batched network call: statistics, and the
-    running-stat updates, stay per call exactly as in train.py:427-442)."""
-    if training:
-        bn.num_batches_tracked += groups
+    running-stat updates, stay per call exactly as in train.py:427-442).  num_batches_tracked of every layer is bumped
+    by one add per network call (ArenaNet._nbt, see encoder_forward)."""
     return O.bn_apply(y, sums if training else None, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
                       residual, (1 if relu else 0) | O.rnd(), groups)
 
 
 def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
     C = conv.weight.shape[0]
-    sums = torch.zeros(O.BN_SLOTS * groups * C * 2, device=x.device, dtype=torch.float64) if training else None
+    sums = _SUMS.take(O.BN_SLOTS * groups * C * 2, x.device) if training else None
     y = O.conv_fwd(x, conv.w_op(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups)
     z, saved = _bn_fwd(y, sums, bn, training, relu, residual, groups)
     return y, z, saved
@@ -340,7 +378,7 @@ def block_forward(blk, x, training, G=1):
     if blk.downsample is not None:
         r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
     C = last_conv.weight.shape[0]
-    sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=x.device, dtype=torch.float64) if training else None
+    sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x.device) if training else None
     y = O.conv_fwd(last_in, last_conv.w_op(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G)
     out, saved = _bn_fwd(y, sums, last_bn, training, True, sc, G)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
@@ -375,13 +413,22 @@ def encoder_forward(enc, imgs, training, G=1):
     """imgs: tuple of one (DispResNet) or two (PoseResNet, channel-concatenated) NCHW image batches."""
     t = enc.encoder
     rec = {"G": G}
+    if training:
+        _SUMS.begin(imgs[0].device)
+        nbt = getattr(enc, "_nbt", None)
+        if nbt is not None:
+            nbt.add_(G)                      # every BatchNorm layer's num_batches_tracked (views of this tensor)
+        else:
+            for m in enc.modules():
+                if isinstance(m, BNParams):
+                    m.num_batches_tracked += G
     if O.CONFIG["conv_mode"] == "tf32":
         # 7x7 stem on the tensor cores: input channels zero-padded 3 -> 4 / 6 -> 8 (K = 49 * Cpad), weights likewise
         cpad = 4 * len(imgs)
         x_nhwc = O.nchw_to_nhwc_pad(imgs[0], imgs[1] if len(imgs) > 1 else None, cpad)
         w0 = O.pad_channels(t.conv1.w_khwc(), cpad)
         C = w0.shape[0]
-        sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=x_nhwc.device, dtype=torch.float64) if training else None
+        sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x_nhwc.device) if training else None
         rec["y0"] = O.conv_fwd(x_nhwc, w0, None, 2, 3, O.PAD_ZERO, O.ACT_NONE, sums, G)
         f0, rec["s0"] = _bn_fwd(rec["y0"], sums, t.bn1, training, True, None, G)
     else:

@@ -95,11 +95,11 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.restore(snap)
         nnops.invalidate_weight_cache()
-        before = L.STATS["launches"]
+        before = L.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._static_out = torch.stack(self._eager_step(*self._static))
-        self.launches_per_step = L.STATS["launches"] - before
+        self.launches_per_step = L.launch_count() - before
         nnops.invalidate_weight_cache()     # tensors cached during capture belong to the graph's private pool
         self._graph = graph
         L.PROF.update(prof)
