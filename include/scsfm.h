@@ -185,6 +185,9 @@ int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream);
 /* test / experiment hook: enable = 0 routes every layer through the gather kernel; force_mt (1|2 stacked 128-pixel
  * sub-tiles), force_bn (16|32|64|128), force_tw_log2 (3|4) override the tile heuristic, 0 = automatic */
 int scsfm_conv_tma_config(int enable, int force_mt, int force_bn, int force_tw_log2);
+/* profiling hook: device array of 8 x (number of SMs) 64-bit cycle counters written by every later TMA-kernel launch
+ * (producer / MMA-issuer / epilogue wait and total cycles per persistent CTA, see conv_tma.cu), NULL = off */
+int scsfm_conv_tma_debug(unsigned long long* buf);
 int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
 /* stride-2 data gradient: four parity-class weight sets back to back (Cin*kh*kw*Cout floats in total); p->w of
  * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */
