@@ -128,7 +128,7 @@ for (name, B, H, W, Cin, Cout, k, s, pad, reflect, act, has_bias, groups) in FWD
     y0, s0 = run()
     t0 = timeit(lambda: run(False))
     e0 = rel(y0, ref)
-    for cname, cfg in CONFIGS + ([("bn64 mt1", (1, 1, 64, 0)), ("bn64 mt2", (1, 2, 64, 0))] if Cout > 64 else []):
+    for cname, cfg in CONFIGS:
         O.conv_tma_config(*cfg)
         y1, s1 = run()
         torch.cuda.synchronize()
