@@ -193,6 +193,13 @@ int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* 
  * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */
 int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream);
 
+/* Every flip of a network in one launch (the weights change once per optimizer step).  table: device array of
+ * (n_rows + 1) x 12 int64 {src pointer, dst pointer, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, tap step, first block};
+ * one row per scsfm_weight_flip job / per stride-2 parity class with taps (jh x jw taps kept, starting at (dy_max, dx_max)
+ * and walking backwards by `tap step`); a row owns the 1024-element blocks [first block, next row's first block), the
+ * last row is a sentinel whose first block is total_blocks. */
+int scsfm_weight_flip_batched(const long long* table, int n_rows, int total_blocks, void* stream);
+
 /* Disparity heads (DispResNet.py:79-82,98): 3x3 reflection-padded conv with one output channel, exact fp32.
  * in [B,H,W,C], w [9*C] (= [1,3,3,C]), out / dpre [B,H,W]; dw, dbias accumulated into. */
 int scsfm_head_conv_fwd(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int act, void* stream);

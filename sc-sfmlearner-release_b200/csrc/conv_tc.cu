@@ -549,9 +549,12 @@ static int tc_dispatch_gather(const ScsfmConv& p, const TcView& v, cudaStream_t 
 
 static int tc_dispatch(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     if (p.pad_mode == PADMODE_ZERO && conv_tma_eligible(p, v)) return launch_conv_tma(p, v, st);
-    if (p.pad_mode == PADMODE_REFLECT && p.bn_sums == nullptr && p.Ho >= 3 && p.Wo >= 3 && conv_tma_eligible(p, v)) {
+    if (p.pad_mode == PADMODE_REFLECT && p.bn_sums == nullptr && p.Ho >= 3 && p.Wo >= 3 &&
+        (p.Ho * p.Wo >= 64 * 208 || conv_tma_forced()) && conv_tma_eligible(p, v)) {
         // reflection padding only changes the outermost ring of output pixels: run the TMA kernel with zero padding
-        // (interior exact), then recompute the 2*(Ho+Wo)-4 border pixels per image with the reflecting gather kernel
+        // (interior exact), then recompute the 2*(Ho+Wo)-4 border pixels per image with the reflecting gather kernel.
+        // Measured (tools/check_conv_tma.py): pays off from 64x208 upwards; below that the ring is too large a share
+        // of the image and the gather kernel alone is faster.
         ScsfmConv q = p;
         q.pad_mode = PADMODE_ZERO;
         if (int rc = launch_conv_tma(q, v, st)) return rc;
@@ -588,6 +591,50 @@ extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int C
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, kh, kw, kh - 1, kw - 1, 1, wt);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+// All flips of a network in ONE launch.  table = n rows of 12 int64: {src pointer, dst pointer, Co, kh, kw, Ci, jh, jw,
+// dy_max, dx_max, step, first block}; a row is one weight_flip_kernel job (a stride-2 layer contributes one row per parity
+// class with taps) and owns blocks [first block, next row's first block); row n is a sentinel holding the total.
+constexpr int FLIP_PER_BLOCK = 1024;
+__global__ void weight_flip_batched_kernel(const long long* __restrict__ table, int n) {
+    __shared__ int s_row;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n;                       // last row with first block <= blockIdx.x
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (table[mid * 12 + 11] <= (long long)blockIdx.x) lo = mid; else hi = mid;
+        }
+        s_row = lo;
+    }
+    __syncthreads();
+    const long long* e = table + s_row * 12;
+    const float* w = reinterpret_cast<const float*>(e[0]);
+    float* wt = reinterpret_cast<float*>(e[1]);
+    const int Co = (int)e[2], kh = (int)e[3], kw = (int)e[4], Ci = (int)e[5], jh = (int)e[6], jw = (int)e[7];
+    const int dy_max = (int)e[8], dx_max = (int)e[9], step = (int)e[10];
+    const long long total = (long long)Co * jh * jw * Ci;
+    const long long base = ((long long)blockIdx.x - e[11]) * FLIP_PER_BLOCK;
+#pragma unroll
+    for (int k = 0; k < FLIP_PER_BLOCK / 256; ++k) {
+        const long long i = base + k * 256 + threadIdx.x;
+        if (i < total) {
+            const int o = (int)(i % Co);
+            long long t2 = i / Co;
+            const int jx = (int)(t2 % jw); t2 /= jw;
+            const int jy = (int)(t2 % jh);
+            const int c = (int)(t2 / jh);
+            const int dy = dy_max - step * jy, dx = dx_max - step * jx;
+            wt[i] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
+        }
+    }
+}
+
+extern "C" int scsfm_weight_flip_batched(const long long* table, int n_rows, int total_blocks, void* stream) {
+    SCSFM_CHECK_ARG(table != nullptr && n_rows > 0 && total_blocks > 0, "weight_flip_batched: bad arguments");
+    weight_flip_batched_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(table, n_rows);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

@@ -72,6 +72,8 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint8_t* ring = smem + 1024;
+    // epilogue transpose buffer T[64 pixels][BNW + 4] behind the ring and the over-read pad
+    float* T = reinterpret_cast<float*>(ring + (size_t)g.stages * g.stage_bytes + (TBM - BNW) * 128);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
@@ -188,11 +190,19 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 0-7)
-        // TMEM lane = output channel: warp w owns channels n0 + 32*(w%4) + lane and every other 32-pixel chunk (w/4).  The
-        // per-pixel work is kept to a pointer add, a store and the BatchNorm accumulation: the address of an 8-pixel row
-        // segment is computed once, bias / residual / activation are applied to the 32 values in registers beforehand.
+        // ------------------------------------------------------------------ epilogue (warps 0-7, 256 threads)
+        // The accumulator is channel-major (TMEM lane = output channel, column = pixel) but the tensor is NHWC, and a thin
+        // layer occupies only 16 or 32 of the 128 lanes.  So the tile is transposed through shared memory in rounds of 64
+        // pixels: the warps whose lane quarter holds real channels copy tcgen05.ld results into T[pixel][channel], then
+        // ALL 256 threads walk T as float4 channel groups: bias / residual addend / activation / TF32 rounding, 16-byte
+        // coalesced stores, BatchNorm partial sums per thread (a thread always owns the same 4 channels).
+        constexpr int CT = BNW;                      // channels per T row
+        constexpr int TS = CT + 4;                   // row stride in floats (keeps rows 16-byte aligned)
+        constexpr int GPR = CT / 4;                  // float4 groups per pixel
+        constexpr int ITER = (64 * GPR) / 256;       // groups per thread per round (CT / 16)
+        constexpr int PXSTEP = 256 / GPR;            // pixel distance between a thread's groups
         const int quarter = warp & 3, half = warp >> 2;
+        const int c4 = tid % GPR, px0 = tid / GPR;   // this thread's channel group and first pixel of a round
         const int groups = p.bn_groups > 0 ? p.bn_groups : 1;
         const int act = p.act & 0xff;
         const bool round = (p.act & ROUND_TF32) != 0;
@@ -200,7 +210,6 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
         const long long img_step = (long long)v.out_H * v.out_W * N;       // elements between images
         const int row_step = v.out_sy * v.out_W * N;                        // ... between tile rows
         const int px_step = v.out_sx * N;                                   // ... between tile columns
-        const int segs_per_row_log2 = g.tw_log2 - 3;                        // 8-pixel segments per tile row: 1 or 2
         int j = 0;
         long long t_wait = 0, t_ld = 0;
         const long long t_begin = tma_clock();
@@ -216,91 +225,76 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
             if (g.dbg) t_wait += tma_clock() - t0;
             tc::fence_after_thread_sync();
-            const int n = n0 + quarter * 32 + lane;              // this lane's output channel
-            if (n0 + quarter * 32 < N) {                          // warp-uniform: this lane quarter holds real channels
-                const bool n_ok = n < N;
-                const float bias = (p.bias != nullptr && n_ok) ? __ldg(p.bias + n) : 0.f;
-                const uint32_t acc = tmem_base + (uint32_t)(buf * NPIX) + ((uint32_t)(quarter * 32) << 16);
-                const long long tile_off = (long long)b * img_step + (long long)(y0 * v.out_sy + v.out_oy) * (v.out_W * N) +
-                                           (long long)(x0 * v.out_sx + v.out_ox) * N + (n_ok ? n : 0);
-                const bool full = (y0 + MT * TH <= Ho) && (x0 + TW <= Wo);      // no pixel of the tile is masked
-                double s1 = 0.0, s2 = 0.0;
+            const int cv = min(TBM, N - n0);                     // real channels of this Cout tile (multiple of 4)
+            const bool loader = quarter * 32 < cv;                // warp-uniform: this lane quarter holds real channels
+            const bool ch_ok = 4 * c4 < cv;
+            const int n = n0 + 4 * c4;                            // first of this thread's 4 channels
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && ch_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            const uint32_t acc = tmem_base + (uint32_t)(buf * NPIX) + ((uint32_t)(quarter * 32) << 16);
+            const long long tile_off = (long long)b * img_step + (long long)(y0 * v.out_sy + v.out_oy) * (v.out_W * N) +
+                                       (long long)(x0 * v.out_sx + v.out_ox) * N + n;
+            float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-                for (int cc = half; cc < NPIX / 32; cc += TMA_EWARPS / 4) {
+            for (int rd = 0; rd < NPIX / 64; ++rd) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // A: everybody has finished reading the previous round
+                if (loader) {
                     uint32_t r[32];
                     const long long tl0 = g.dbg ? tma_clock() : 0;
-                    tc::tmem_ld32(acc + (uint32_t)(cc * 32), r);
+                    tc::tmem_ld32(acc + (uint32_t)((2 * rd + half) * 32), r);
                     tc::tmem_ld_wait();
                     if (g.dbg) t_ld += tma_clock() - tl0;
-                    // the chunk = four 8-pixel row segments; segment sg starts at tile row lrow, tile column lcol
-                    long long seg_off[4];
-                    unsigned okm = 0;                       // bit (8*sg + c): pixel is inside the image
+                    float* dst = T + (32 * half) * TS + quarter * 32 + lane;
+                    if (quarter * 32 + lane < CT) {            // (a 16-channel tile only has 16 real lanes)
 #pragma unroll
-                    for (int sg = 0; sg < 4; ++sg) {
-                        const int sidx = cc * 4 + sg;
-                        const int lrow = sidx >> segs_per_row_log2, lcol = (sidx & ((1 << segs_per_row_log2) - 1)) * 8;
-                        seg_off[sg] = tile_off + (long long)lrow * row_step + (long long)lcol * px_step;
-                        if (full) okm |= 0xffu << (8 * sg);
-                        else if (y0 + lrow < Ho) {
-                            const int left = Wo - (x0 + lcol);                 // columns of this segment inside the image
-                            okm |= (left >= 8 ? 0xffu : (left > 0 ? (1u << left) - 1u : 0u)) << (8 * sg);
-                        }
+                        for (int i = 0; i < 32; ++i) dst[i * TS] = __uint_as_float(r[i]);     // consecutive lanes = consecutive words
                     }
-                    float x[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) + bias;
-                    if (p.addend != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (n_ok && ((okm >> i) & 1u)) x[i] += __ldg(p.addend + seg_off[i >> 3] + (long long)(i & 7) * px_step);
-                    }
-                    if (act == ACT_RELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-                    } else if (act == ACT_ELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = x[i] > 0.f ? x[i] : expm1f(x[i]);
-                    } else if (act == ACT_DISP) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = 10.0f * (1.0f / (1.0f + expf(-x[i]))) + 0.01f;
-                    }
-                    if (round) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = tf32_round(x[i]);
-                    }
-                    float c1 = 0.f, c2 = 0.f;
-                    if (n_ok) {
-#pragma unroll
-                        for (int sg = 0; sg < 4; ++sg) {
-                            float* dst = p.out + seg_off[sg];
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                if ((okm >> (8 * sg + c)) & 1u) {       // warp-uniform
-                                    const float xv = x[8 * sg + c];
-                                    *dst = xv;                          // 32 lanes = 32 consecutive channels: one 128-byte line
-                                    c1 += xv;
-                                    c2 += xv * xv;
-                                }
-                                dst += px_step;
-                            }
-                        }
-                    }
-                    s1 += (double)c1;
-                    s2 += (double)c2;
                 }
-                if (p.bn_sums != nullptr && n_ok) {
-                    // BatchNorm sums: lane = channel, so the column sums are plain per-lane accumulations (fp32 over the 32
-                    // pixels of a chunk, fp64 from there on); the tile lies in one image, hence in one BatchNorm group
-                    const int grp = b / (p.B / groups);
-                    double* d = p.bn_sums + (((size_t)(w % SCSFM_BN_SLOTS) * groups + grp) * N + n) * 2;
-                    atomicAdd(d, s1);
-                    atomicAdd(d + 1, s2);
+                if (rd == NPIX / 64 - 1) tc::fence_before_thread_sync();
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // B: the round's 64 x cv values are in T
+                if (rd == NPIX / 64 - 1 && lane == 0) tc::mbar_arrive(acc_empty + buf);      // every tcgen05.ld of the tile is done
+#pragma unroll
+                for (int k = 0; k < ITER; ++k) {
+                    const int px = px0 + k * PXSTEP;
+                    const int l = rd * 64 + px;                 // pixel index inside the tile
+                    const int row = l >> g.tw_log2, col = l & (TW - 1);
+                    if (ch_ok && y0 + row < Ho && x0 + col < Wo) {
+                        float4 x = *reinterpret_cast<const float4*>(T + px * TS + 4 * c4);
+                        x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+                        const long long off = tile_off + (long long)row * row_step + (long long)col * px_step;
+                        if (p.addend != nullptr) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(p.addend + off));
+                            x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+                        }
+                        if (act != ACT_NONE) { x.x = tc_act(x.x, act); x.y = tc_act(x.y, act); x.z = tc_act(x.z, act); x.w = tc_act(x.w, act); }
+                        if (round) { x.x = tf32_round(x.x); x.y = tf32_round(x.y); x.z = tf32_round(x.z); x.w = tf32_round(x.w); }
+                        *reinterpret_cast<float4*>(p.out + off) = x;
+                        bs1[0] += x.x; bs1[1] += x.y; bs1[2] += x.z; bs1[3] += x.w;
+                        bs2[0] += x.x * x.x; bs2[1] += x.y * x.y; bs2[2] += x.z * x.z; bs2[3] += x.w * x.w;
+                    }
                 }
             }
-            // all of this warp's tcgen05.ld of the buffer have completed (tmem_ld_wait above): hand it back to the MMA warp
-            tc::fence_before_thread_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+            if (p.bn_sums != nullptr) {
+                // lanes l, l + GPR, l + 2 GPR ... of a warp own the same 4 channels: butterfly them together, then one fp64
+                // atomic pair per (warp, channel).  The tile lies in one image, hence in one BatchNorm group.
+#pragma unroll
+                for (int o = GPR; o < 32; o <<= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        bs1[q] += __shfl_xor_sync(0xffffffffu, bs1[q], o);
+                        bs2[q] += __shfl_xor_sync(0xffffffffu, bs2[q], o);
+                    }
+                }
+                if (lane < GPR && ch_ok) {
+                    const int grp = b / (p.B / groups);
+                    double* d = p.bn_sums + (((size_t)(w % SCSFM_BN_SLOTS) * groups + grp) * N + n) * 2;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        atomicAdd(d + 2 * q, (double)bs1[q]);
+                        atomicAdd(d + 2 * q + 1, (double)bs2[q]);
+                    }
+                }
+            }
         }
         if (g.dbg && tid == 0) {
             g.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_wait;
@@ -327,10 +321,12 @@ static unsigned long long* g_dbg = nullptr;
 bool conv_tma_eligible(const ScsfmConv& p, const TcView& v) {
     if (!g_tma_enable || v.border) return false;
     if (v.in_stride != 1 || v.kh > TMA_MAX_KH || v.kw > TMA_MAX_KH || v.kh < 1 || v.kw < 1) return false;
-    if ((p.Cin & 3) != 0) return false;
+    if ((p.Cin & 3) != 0 || (p.Cout & 3) != 0) return false;      // 16-byte TMA rows / float4 epilogue
     if (p.bn_sums && p.B % (p.bn_groups > 0 ? p.bn_groups : 1) != 0) return false;
     return true;
 }
+
+bool conv_tma_forced() { return g_force_mt != 0 || g_force_bn != 0 || g_force_tw != 0; }
 
 static int sm_count() {
     static int n = 0;
@@ -357,8 +353,9 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
     g.num_work = g.tiles_x * g.tiles_y * p.B * g.n_tiles;
     g.a_bytes = ((MT * TH + v.kh - 1) * TW * 128 + 1023) / 1024 * 1024;
     g.stage_bytes = g.a_bytes + v.kh * BNW * 128;
-    // 1024 alignment slack + 1024 barrier block + ring + the MMA's over-read past a BNW-row weight tile (M = 128 rows)
-    const int fixed = 1024 + 1024 + (TBM - BNW) * 128;
+    // 1024 alignment slack + 1024 barrier block + ring + the MMA's over-read past a BNW-row weight tile (M = 128 rows) +
+    // the epilogue's transpose buffer T[64][BNW + 4]
+    const int fixed = 1024 + 1024 + (TBM - BNW) * 128 + 64 * (BNW + 4) * 4;
     g.stages = (TMA_SMEM_MAX - fixed) / g.stage_bytes;
     if (g.stages > TMA_MAX_STAGES) g.stages = TMA_MAX_STAGES;
     if (g.stages < 2) {
@@ -412,21 +409,21 @@ int launch_conv_tma(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     else if (N <= 32) bnw = 32;
     else if (N <= 64) bnw = 64;
     else bnw = 128;
-    // Pixel tile: 1 or 2 stacked 128-pixel sub-tiles (N = 128 / 256 of the MMA), TW = 8 or 16.  An MMA costs about the
-    // same for N = 128 and N = 256, so the cost is the number of (padded) tiles, inflated by the fraction of the
-    // persistent CTAs' last wave that idles and, slightly, by the halo rows each tile re-reads.
+    // Pixel tile: 1 or 2 stacked 128-pixel sub-tiles (N = 128 / 256 of the MMA), TW = 8 or 16.  An MMA costs the same
+    // for N = 128 and N = 256 (measured), so a tile costs the same either way: minimise the number of waves of the
+    // persistent CTAs, then the padded area (halo rows included), then prefer the smaller tile.
     const int nsm = sm_count();
     const long nt = (N + TBM - 1) / TBM;
-    int best_mt = 2, best_tw = 4;
+    int best_mt = 1, best_tw = 4;
     double best_cost = -1.0;
     for (int mt = 1; mt <= 2; ++mt)
-        for (int twl = 3; twl <= 4; ++twl) {
+        for (int twl = 4; twl >= 3; --twl) {
             const int tw = 1 << twl, th = mt * (TBM >> twl);
             const long ty = (p.Ho + th - 1) / th, tx = (p.Wo + tw - 1) / tw;
             const long work = ty * tx * p.B * nt;
             const long waves = (work + nsm - 1) / nsm;
-            const double halo = 1.0 + 0.25 * (double)(v.kh - 1) / th;
-            const double cost = (double)waves * halo;
+            const double area = (double)(ty * (th + v.kh - 1)) * (double)(tx * tw) / ((double)p.Ho * p.Wo);     // >= 1
+            const double cost = (double)waves + 0.05 * area + 0.01 * mt;
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_mt = mt; best_tw = twl; }
         }
     if (g_force_mt) best_mt = g_force_mt;

@@ -251,9 +251,11 @@ class ArenaNet(nn.Module):
 
     def refresh_operand_weights(self):
         """Start of every network call: the weights may have changed since the last one (optimizer, load_state_dict)."""
-        O.invalidate_weight_cache()
         if O.CONFIG["conv_mode"] == "tf32":
             O.round_tf32(self._flat, self._flat_tf32)
+            # flipped / transposed copies for the data gradients: all of them in one launch, in place
+            lo = self._flat_tf32.data_ptr()
+            O.refresh_flips(lo, lo + 4 * self._flat_tf32.numel(), self._flat_tf32.device)
 
     def _attach_grads(self):
         """Called at the start of every backward: if an optimizer dropped the gradients
@@ -686,7 +688,7 @@ class ArenaAdam:
             m, v, _ = self.state[id(n)]
             O.adam_step(n._flat, n._flat_grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                         0, self._step)
-        O.invalidate_weight_cache()        # flipped dgrad weights are stale after the update
+        # (the TF32 mirror and the flipped dgrad weights are refreshed at the start of the next network call)
 
     def snapshot(self):
         """Copies of everything a step mutates (used to undo the warm-up step before CUDA-graph capture)."""
@@ -704,7 +706,6 @@ class ArenaAdam:
             n._flat.copy_(flat); m.copy_(m0); v.copy_(v0)
             for k, b in n.named_buffers():
                 b.copy_(bufs[k])
-        O.invalidate_weight_cache()
 
     def state_dict(self):
         self._ensure_state()

@@ -44,6 +44,7 @@ def _lib():
         if hasattr(lib, "scsfm_weight_flip"):
             lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
             lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, P]
+            lib.scsfm_weight_flip_batched.argtypes = [P, I, I, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_head_conv_fwd.argtypes = [P, P, P, P, I, I, I, I, I, P]
@@ -102,12 +103,31 @@ def tc_supported(kind, Cin, Cout, kh, stride):
     return False
 
 
-_flip_cache = {}
+_flip_cache = {}          # (weight pointer, shape, stride, pad) -> flipped weights (persistent buffers)
+_flip_tables = []         # live FlipTable objects (one per network arena)
+FLIP_BLOCK = 1024         # elements per block of scsfm_weight_flip_batched
+
+
+def _s2_classes(kh, kw, pad):
+    """Parity classes (py, px) of a stride-2 data gradient: taps kept = jh x jw starting at (dy_max, dx_max), step 2."""
+    out = []
+    for py in range(2):
+        for px in range(2):
+            dy_max, dx_max = kh - 1, kw - 1
+            while dy_max >= 0 and ((py + pad - dy_max) & 1):
+                dy_max -= 1
+            while dx_max >= 0 and ((px + pad - dx_max) & 1):
+                dx_max -= 1
+            jh = 0 if dy_max < 0 else dy_max // 2 + 1
+            jw = 0 if dx_max < 0 else dx_max // 2 + 1
+            out.append((jh, jw, dy_max, dx_max))
+    return out
 
 
 def flipped_weights(w, stride=1, pad=0):
     """[Cout,kh,kw,Cin] -> weights of the transposed conv ([Cin,kh,kw,Cout], reversed taps; for stride 2 the four
-    parity-class tap subsets back to back), TF32-rounded, cached per weight tensor until `invalidate_weight_cache()`."""
+    parity-class tap subsets back to back), TF32-rounded.  Cached per weight tensor; the cache entry is refreshed in
+    place by refresh_flips() (one launch per network and step) or dropped by invalidate_weight_cache()."""
     key = (w.data_ptr(), tuple(w.shape), stride, pad)
     wt = _flip_cache.get(key)
     if wt is None:
@@ -123,8 +143,46 @@ def flipped_weights(w, stride=1, pad=0):
     return wt
 
 
+class FlipTable:
+    """Device job table of every cached flip whose source weights live in [lo, hi) (one network's operand arena)."""
+
+    def __init__(self, lo, hi, device):
+        self.lo, self.hi = lo, hi
+        self.keys = sorted(k for k in _flip_cache if lo <= k[0] < hi)
+        rows, blk = [], 0
+        for key in self.keys:
+            ptr, (Cout, kh, kw, Cin), stride, pad = key
+            dst = _flip_cache[key].data_ptr()
+            jobs = [(kh, kw, kh - 1, kw - 1)] if stride == 1 else _s2_classes(kh, kw, pad)
+            for (jh, jw, dy_max, dx_max) in jobs:
+                total = Cout * jh * jw * Cin
+                if total > 0:
+                    rows.append([ptr, dst, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, stride, blk])
+                    blk += (total + FLIP_BLOCK - 1) // FLIP_BLOCK
+                dst += 4 * total
+        self.n_rows, self.total_blocks, self.bytes = len(rows), blk, 8.0 * sum(_flip_cache[k].numel() for k in self.keys)
+        rows.append([0] * 11 + [blk])
+        self.table = torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def refresh_flips(lo, hi, device):
+    """The weights in [lo, hi) have changed: recompute every cached flip of them with one launch."""
+    keys = sorted(k for k in _flip_cache if lo <= k[0] < hi)
+    if not keys:
+        return
+    tab = next((t for t in _flip_tables if t.lo == lo and t.hi == hi), None)
+    if tab is None or tab.keys != keys:
+        if tab is not None:
+            _flip_tables.remove(tab)
+        tab = FlipTable(lo, hi, device)
+        _flip_tables.append(tab)
+    L.launch(_lib().scsfm_weight_flip_batched, "scsfm_weight_flip_batched", "weight_flip", 1, tab.bytes, L.ptr(tab.table), tab.n_rows,
+             tab.total_blocks, L.stream())
+
+
 def invalidate_weight_cache():
     _flip_cache.clear()
+    del _flip_tables[:]
 
 
 def conv_desc(x_shape, w, stride, pad, pad_mode, act):

@@ -81,7 +81,6 @@ class Trainer:
         kernel launches become a single graph launch.  One eager warm-up step runs first (lazy allocations,
         Adam state) and is undone, so capturing does not advance training.  Single-GPU path."""
         from . import lib as L
-        from . import nnops
         if self.exchange is not None:
             raise RuntimeError("graph capture of the data-parallel step is not enabled")
         self._static = (tgt_img.clone(), [r.clone() for r in ref_imgs], intrinsics.clone())
@@ -94,13 +93,13 @@ class Trainer:
             self._eager_step(*self._static)
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.restore(snap)
-        nnops.invalidate_weight_cache()
+        # the warm-up step left the persistent flipped-weight buffers and their job tables in place: the capture below
+        # records one batched refresh per network instead of one flip per layer
         before = L.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._static_out = torch.stack(self._eager_step(*self._static))
         self.launches_per_step = L.launch_count() - before
-        nnops.invalidate_weight_cache()     # tensors cached during capture belong to the graph's private pool
         self._graph = graph
         L.PROF.update(prof)
 

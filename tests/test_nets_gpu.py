@@ -301,14 +301,22 @@ TC_CASES = [
 ]
 
 
+# (enable, force_mt, force_bn, force_tw_log2) of scsfm_conv_tma_config: the heuristic, the cp.async gather kernel alone,
+# and two forced tilings of the persistent TMA kernel (128 / 256 pixels per MMA, 8- / 16-pixel-wide tiles; forcing also
+# sends small reflection-padded layers through the zero-padded TMA pass + border-ring pass)
+TMA_CONFIGS = {"auto": (1, 0, 0, 0), "gather": (0, 0, 0, 0), "tma-128px-tw8": (1, 1, 0, 3), "tma-256px-tw16": (1, 2, 0, 4)}
+
+
+@pytest.mark.parametrize("tma", sorted(TMA_CONFIGS))
 @pytest.mark.parametrize("case", TC_CASES)
-def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
+def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case, tma):
     """TF32 tensor-core kernels: inputs rounded to 10-bit mantissas by the hardware, fp32 accumulation.
     Operands are rounded to nearest TF32 in the loaders: expected relative L2 error ~3e-4; bound 1e-3."""
     from scsfm import lib as L
     O = _ops()
     if not hasattr(L.load(), "scsfm_conv2d_fwd_tc"):
         pytest.skip("tensor-core kernels not built")
+    O.conv_tma_config(*TMA_CONFIGS[tma])
     B, H, W, Cin, Cout, k, stride, pad, pad_mode, act, bias = case
     g = torch.Generator().manual_seed(11)
     x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
@@ -359,6 +367,7 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case):
     finally:
         O.CONFIG["conv_mode"] = old
         O.invalidate_weight_cache()
+        O.conv_tma_config(1)
 
 
 def test_disp_net_tf32_mode_vs_oracle(golden_nets):

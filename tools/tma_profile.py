@@ -18,6 +18,9 @@ NSM = torch.cuda.get_device_properties(0).multi_processor_count
 CASES = [  # name, B, H, W, Cin, Cout, k, bn_groups, cfg
     ("enc L1 nobn", 12, 64, 208, 64, 64, 3, 0, (1, 2, 0, 0)),
     ("dec 0_1", 12, 256, 832, 16, 16, 3, 0, (1, 2, 0, 0)),
+    ("enc L1", 12, 64, 208, 64, 64, 3, 3, (1, 2, 0, 0)),
+    ("enc L2", 12, 32, 104, 128, 128, 3, 3, (1, 2, 0, 0)),
+    ("dec 1_1", 12, 128, 416, 96, 32, 3, 0, (1, 2, 0, 0)),
 ]
 _UNUSED = [
     ("enc L1", 12, 64, 208, 64, 64, 3, 3, (1, 1, 0, 0)),
