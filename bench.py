@@ -204,6 +204,14 @@ def run_ours(args):
         achieved = dom_work / (dom_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": None}
+    try:        # measured DRAM traffic per launch of the family's kernels (ncu capture summarised by tools/ncu_summarise.py)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_by_family.json")))
+        if dominant in tr:
+            roof["traffic"] = tr[dominant]["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["_source"]
+            roof["algorithmic_bytes_or_flops_per_launch"] = round(dom_work / max(dom_n, 1))
+    except (OSError, ValueError, KeyError):
+        pass
     roof.update(kernel=dominant, launches_timed=dom_n, avg_launch_us=round(1e3 * dom_ms / max(dom_n, 1), 2),
                 share_of_step=round(dom_ms / ms_eager, 4), peak_source=peaks["source"],
                 note="achieved = algorithmic FLOPs (2*M*N*K per conv pass) or bytes of the family / its CUDA-event time over the "
