@@ -196,14 +196,16 @@ int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int 
 /* Every flip of a network in one launch (the weights change once per optimizer step).  table: device array of
  * (n_rows + 1) x 12 int64 {src pointer, dst pointer, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, tap step, first block};
  * one row per scsfm_weight_flip job / per stride-2 parity class with taps (jh x jw taps kept, starting at (dy_max, dx_max)
- * and walking backwards by `tap step`); a row owns the 1024-element blocks [first block, next row's first block), the
- * last row is a sentinel whose first block is total_blocks. */
+ * and walking backwards by `tap step`); a row owns ceil(Cout/32) * ceil(Cin/32) * jh * jw blocks (one 32 x 32 tile
+ * of one tap each) starting at its first block; the last row is a sentinel whose first block is total_blocks. */
 int scsfm_weight_flip_batched(const long long* table, int n_rows, int total_blocks, void* stream);
 
 /* Disparity heads (DispResNet.py:79-82,98): 3x3 reflection-padded conv with one output channel, exact fp32.
  * in [B,H,W,C], w [9*C] (= [1,3,3,C]), out / dpre [B,H,W]; dw, dbias accumulated into. */
 int scsfm_head_conv_fwd(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int act, void* stream);
 int scsfm_head_conv_wgrad(const float* in, const float* dpre, float* dw, float* dbias, int B, int H, int W, int C, void* stream);
+/* gradient w.r.t. the reflection-PADDED head input, dpad [B,H+2,W+2,C] (overwritten; fold it with scsfm_fold_bwd) */
+int scsfm_head_conv_dgrad(const float* dpre, const float* w, float* dpad, int B, int H, int W, int C, void* stream);
 
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
 int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);
@@ -259,9 +261,11 @@ int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale,
 int scsfm_round_tf32(const float* in, float* out, long long n, void* stream);
 
 /* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena.  The 1-based step count is
- * `step`, or *step_dev (device int) when step_dev != NULL so that a captured CUDA graph stays valid. */
+ * `step`, or *step_dev (device int) when step_dev != NULL so that a captured CUDA graph stays valid.
+ * param_tf32 (optional): receives the updated parameters rounded to TF32 (the tensor-core convolutions' operand copy). */
 int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                    float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream);
+                    float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                    float* param_tf32, void* stream);
 
 #ifdef __cplusplus
 }

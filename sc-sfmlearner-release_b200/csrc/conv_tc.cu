@@ -598,9 +598,12 @@ extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int C
 // All flips of a network in ONE launch.  table = n rows of 12 int64: {src pointer, dst pointer, Co, kh, kw, Ci, jh, jw,
 // dy_max, dx_max, step, first block}; a row is one weight_flip_kernel job (a stride-2 layer contributes one row per parity
 // class with taps) and owns blocks [first block, next row's first block); row n is a sentinel holding the total.
-constexpr int FLIP_PER_BLOCK = 1024;
-__global__ void weight_flip_batched_kernel(const long long* __restrict__ table, int n) {
+// Each block transposes one 32 (Cout) x 32 (Cin) tile of one tap through shared memory: reads coalesced along Cin, writes
+// coalesced along Cout.  A row owns ceil(Co/32) * ceil(Ci/32) * jh * jw blocks.
+__global__ void __launch_bounds__(256)
+weight_flip_batched_kernel(const long long* __restrict__ table, int n) {
     __shared__ int s_row;
+    __shared__ float tile[32][33];
     if (threadIdx.x == 0) {
         int lo = 0, hi = n;                       // last row with first block <= blockIdx.x
         while (hi - lo > 1) {
@@ -615,20 +618,23 @@ __global__ void weight_flip_batched_kernel(const long long* __restrict__ table, 
     float* wt = reinterpret_cast<float*>(e[1]);
     const int Co = (int)e[2], kh = (int)e[3], kw = (int)e[4], Ci = (int)e[5], jh = (int)e[6], jw = (int)e[7];
     const int dy_max = (int)e[8], dx_max = (int)e[9], step = (int)e[10];
-    const long long total = (long long)Co * jh * jw * Ci;
-    const long long base = ((long long)blockIdx.x - e[11]) * FLIP_PER_BLOCK;
+    const int tco = (Co + 31) >> 5, tci = (Ci + 31) >> 5;
+    int t = (int)((long long)blockIdx.x - e[11]);
+    const int to = t % tco; t /= tco;
+    const int tc = t % tci; t /= tci;
+    const int jy = t / jw, jx = t - jy * jw;
+    const int dy = dy_max - step * jy, dx = dx_max - step * jx;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < FLIP_PER_BLOCK / 256; ++k) {
-        const long long i = base + k * 256 + threadIdx.x;
-        if (i < total) {
-            const int o = (int)(i % Co);
-            long long t2 = i / Co;
-            const int jx = (int)(t2 % jw); t2 /= jw;
-            const int jy = (int)(t2 % jh);
-            const int c = (int)(t2 / jh);
-            const int dy = dy_max - step * jy, dx = dx_max - step * jx;
-            wt[i] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
-        }
+    for (int k = 0; k < 4; ++k) {
+        const int o = to * 32 + ty + 8 * k, c = tc * 32 + tx;
+        if (o < Co && c < Ci) tile[ty + 8 * k][tx] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = tc * 32 + ty + 8 * k, o = to * 32 + tx;
+        if (c < Ci && o < Co) wt[(((size_t)c * jh + jy) * jw + jx) * Co + o] = tile[tx][ty + 8 * k];
     }
 }
 

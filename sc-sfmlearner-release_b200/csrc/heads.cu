@@ -20,7 +20,9 @@ head_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const
         const int x = (int)(p % W);
         const long long t = p / W;
         const int y = (int)(t % H), b = (int)(t / H);
-        float acc = bias ? __ldg(bias) : 0.f;
+        // four independent accumulation chains (one per float4 component): a single chain of 9*C dependent FMAs is
+        // latency-bound at ~4 cycles each
+        float4 acc4 = make_float4(bias ? __ldg(bias) : 0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
             const int yy = reflect_index(y + dy, H);
@@ -29,12 +31,14 @@ head_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const
                 const int xx = reflect_index(x + dx, W);
                 const float4* src = reinterpret_cast<const float4*>(in + (((size_t)b * H + yy) * W + xx) * C);
                 const float4* ws = reinterpret_cast<const float4*>(sw + ((dy + 1) * 3 + dx + 1) * C);
+#pragma unroll 4
                 for (int c = 0; c < C4; ++c) {
                     const float4 a = __ldg(src + c), k = ws[c];
-                    acc = fmaf(a.x, k.x, acc); acc = fmaf(a.y, k.y, acc); acc = fmaf(a.z, k.z, acc); acc = fmaf(a.w, k.w, acc);
+                    acc4.x = fmaf(a.x, k.x, acc4.x); acc4.y = fmaf(a.y, k.y, acc4.y); acc4.z = fmaf(a.z, k.z, acc4.z); acc4.w = fmaf(a.w, k.w, acc4.w);
                 }
             }
         }
+        float acc = (acc4.x + acc4.y) + (acc4.z + acc4.w);
         if ((act & 0xff) == ACT_DISP) acc = 10.0f * (1.0f / (1.0f + expf(-acc))) + 0.01f;
         out[p] = acc;
     }
@@ -101,6 +105,40 @@ head_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dpre, 
     }
 }
 
+// Gradient w.r.t. the reflection-PADDED input of the head: dpad[b][qy][qx][c] = sum_{dy,dx} dpre[b][qy-dy][qx-dx] * w[dy][dx][c]
+// over the taps whose source pixel exists ([B,H+2,W+2,C], folded onto the unpadded tensor by scsfm_fold_bwd).
+// thread = (padded pixel, 4-channel chunk); 9 broadcast loads of dpre, one 16-byte store: write-bandwidth bound.
+__global__ void __launch_bounds__(HT)
+head_dgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dpad, int B, int H, int W, int C) {
+    extern __shared__ float sw[];        // [9][C]
+    for (int i = threadIdx.x; i < 9 * C; i += HT) sw[i] = w[i];
+    __syncthreads();
+    const int C4 = C >> 2, Hp = H + 2, Wp = W + 2;
+    const long long total = (long long)B * Hp * Wp * C4;
+    for (long long i = blockIdx.x * (long long)HT + threadIdx.x; i < total; i += (long long)gridDim.x * HT) {
+        const int c4 = (int)(i % C4);
+        long long t = i / C4;
+        const int qx = (int)(t % Wp); t /= Wp;
+        const int qy = (int)(t % Hp);
+        const int b = (int)(t / Hp);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = qy - dy;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int x = qx - dx;
+                if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+                    const float g = __ldg(dpre + ((size_t)b * H + y) * W + x);
+                    const float4 k = *reinterpret_cast<const float4*>(sw + (dy * 3 + dx) * C + 4 * c4);
+                    acc.x = fmaf(g, k.x, acc.x); acc.y = fmaf(g, k.y, acc.y); acc.z = fmaf(g, k.z, acc.z); acc.w = fmaf(g, k.w, acc.w);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(dpad + i * 4) = acc;
+    }
+}
+
 }  // namespace scsfm
 
 using namespace scsfm;
@@ -124,6 +162,16 @@ extern "C" int scsfm_head_conv_wgrad(const float* in, const float* dpre, float* 
     if (g > 148 * 4) g = 148 * 4;
     if (g < 1) g = 1;
     head_wgrad_kernel<<<(int)g, HT, 0, (cudaStream_t)stream>>>(in, dpre, dw, dbias, B, H, W, C);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+extern "C" int scsfm_head_conv_dgrad(const float* dpre, const float* w, float* dpad, int B, int H, int W, int C, void* stream) {
+    SCSFM_CHECK_ARG(dpre && w && dpad && B > 0 && H >= 2 && W >= 2 && C >= 4 && (C & 3) == 0 && C <= 1024, "head_conv_dgrad: bad arguments");
+    const long long total = (long long)B * (H + 2) * (W + 2) * (C / 4);
+    long long g = (total + HT - 1) / HT;
+    if (g > 148 * 32) g = 148 * 32;
+    head_dgrad_kernel<<<(int)g, HT, 9 * C * sizeof(float), (cudaStream_t)stream>>>(dpre, w, dpad, B, H, W, C);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

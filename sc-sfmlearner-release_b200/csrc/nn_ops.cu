@@ -560,7 +560,7 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
 // ----- Adam ---------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, int step_host,
-                            const int* __restrict__ step_dev) {
+                            const int* __restrict__ step_dev, float* __restrict__ p_tf32) {
     // torch.optim.Adam (non-amsgrad): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
     // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  The step count may live on the device so that a captured
     // CUDA graph of the training step stays valid across replays.
@@ -576,7 +576,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
         m[i] = mm;
         v[i] = vv;
-        p[i] = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        const float pn = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        p[i] = pn;
+        if (p_tf32 != nullptr) p_tf32[i] = tf32_round(pn);      // operand mirror of the tensor-core convolutions
     }
 }
 
@@ -769,9 +771,9 @@ extern "C" int scsfm_round_tf32(const float* in, float* out, long long n, void* 
 
 extern "C" int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                               void* stream) {
+                               float* param_tf32, void* stream) {
     SCSFM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
-    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev);
+    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev, param_tf32);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

@@ -240,6 +240,7 @@ class ArenaNet(nn.Module):
                     m._nbt = nbt
         # TF32-rounded mirror of the parameter arena (refreshed at the start of every network call in tf32 mode)
         self._flat_tf32 = torch.zeros_like(flat)
+        self._tf32_version = None
         off = 0
         mods = {id(m.weight): m for m in self.modules() if isinstance(m, ConvParams)}
         for p in params:
@@ -249,10 +250,23 @@ class ArenaNet(nn.Module):
                 mods[id(p)]._tc_view = self._flat_tf32[off:off + cnt].view(O_, kh, kw, I_)
             off += _aligned(cnt)
 
+    trust_adam_mirror = False      # see refresh_operand_weights
+    _tf32_version = None
+
+    def _versions(self):
+        """torch version counters of the arena and of every parameter (in-place updates bump them)."""
+        return (self._flat._version, sum(p._version for p, _ in self._views))
+
     def refresh_operand_weights(self):
         """Start of every network call: the weights may have changed since the last one (optimizer, load_state_dict)."""
         if O.CONFIG["conv_mode"] == "tf32":
-            O.round_tf32(self._flat, self._flat_tf32)
+            # TF32 operand mirror: ArenaAdam writes it together with the parameters (and records the arena's torch
+            # version counter); any other in-place change of the parameters bumps that counter -> re-round here
+            # (the shortcut is opt-in -- Trainer sets trust_adam_mirror -- because writes through `.data` are invisible to
+            # the version counters; without it the mirror is re-rounded on every call)
+            if not (self.trust_adam_mirror and self._tf32_version == self._versions()):
+                O.round_tf32(self._flat, self._flat_tf32)
+                self._tf32_version = self._versions()
             # flipped / transposed copies for the data gradients: all of them in one launch, in place
             lo = self._flat_tf32.data_ptr()
             O.refresh_flips(lo, lo + 4 * self._flat_tf32.numel(), self._flat_tf32.device)
@@ -566,7 +580,7 @@ class DispResNet(ArenaNet):
                 disp = rec["disps"][i]
                 dpre = O.act_bwd_(d_disp[i].reshape(disp.shape).clone(), disp, O.ACT_DISP)
                 O.head_wgrad(b, dpre, g(dc.weight), dc.bias.grad)
-                dpad = O.conv_dgrad(dpre, dc.w_op(), b.shape, 1, 1, None, padded_input=True)
+                dpad = O.head_dgrad(dpre, dc.w_khwc(), b.shape)
                 if not have:
                     d_b = torch.empty_like(b)
                 O.fold_plain(dpad, d_b, b, O.ACT_ELU | O.rnd(), accumulate=have)
@@ -686,8 +700,12 @@ class ArenaAdam:
         self._step += 1
         for n in self.nets:
             m, v, _ = self.state[id(n)]
+            mirror = n._flat_tf32 if O.CONFIG["conv_mode"] == "tf32" else None
             O.adam_step(n._flat, n._flat_grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                        0, self._step)
+                        0, self._step, mirror)
+            # the kernel writes through raw pointers (no torch version bump): with the mirror written the arena is in sync,
+            # without it the next network call must re-round
+            n._tf32_version = n._versions() if mirror is not None else None
         # (the TF32 mirror and the flipped dgrad weights are refreshed at the start of the next network call)
 
     def snapshot(self):

@@ -49,6 +49,7 @@ def _lib():
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_head_conv_fwd.argtypes = [P, P, P, P, I, I, I, I, I, P]
         lib.scsfm_head_conv_wgrad.argtypes = [P, P, P, P, I, I, I, I, P]
+        lib.scsfm_head_conv_dgrad.argtypes = [P, P, P, I, I, I, I, P]
         lib.scsfm_nchw_to_nhwc_pad.argtypes = [P, P, I, I, I, I, I, P, P]
         lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_unpad_add.argtypes = [P, LL, I, I, P, P]
@@ -62,7 +63,7 @@ def _lib():
         lib.scsfm_act_bwd.argtypes = [P, P, LL, I, P]
         lib.scsfm_spatial_mean_fwd.argtypes = [P, I, I, I, F, P, P]
         lib.scsfm_spatial_mean_bwd.argtypes = [P, I, I, I, F, P, P]
-        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P]
+        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P, P]
         _bound = True
     return lib
 
@@ -105,7 +106,6 @@ def tc_supported(kind, Cin, Cout, kh, stride):
 
 _flip_cache = {}          # (weight pointer, shape, stride, pad) -> flipped weights (persistent buffers)
 _flip_tables = []         # live FlipTable objects (one per network arena)
-FLIP_BLOCK = 1024         # elements per block of scsfm_weight_flip_batched
 
 
 def _s2_classes(kh, kw, pad):
@@ -158,7 +158,7 @@ class FlipTable:
                 total = Cout * jh * jw * Cin
                 if total > 0:
                     rows.append([ptr, dst, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, stride, blk])
-                    blk += (total + FLIP_BLOCK - 1) // FLIP_BLOCK
+                    blk += ((Cout + 31) // 32) * ((Cin + 31) // 32) * jh * jw      # one block per 32x32 tile of one tap
                 dst += 4 * total
         self.n_rows, self.total_blocks, self.bytes = len(rows), blk, 8.0 * sum(_flip_cache[k].numel() for k in self.keys)
         rows.append([0] * 11 + [blk])
@@ -259,6 +259,15 @@ def head_fwd(x, w, bias, act):
     L.launch(_lib().scsfm_head_conv_fwd, "scsfm_head_conv_fwd", "head_fwd", 1, 4.0 * x.numel(), L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out),
              B, H, W, C, act, L.stream())
     return out
+
+
+def head_dgrad(dpre, w, x_shape):
+    """Gradient of the disparity head w.r.t. its reflection-padded input: dpre [B,H,W,1], w [1,3,3,C] -> [B,H+2,W+2,C]."""
+    B, H, W, C = x_shape
+    dpad = empty((B, H + 2, W + 2, C), dpre)
+    L.launch(_lib().scsfm_head_conv_dgrad, "scsfm_head_conv_dgrad", "head_dgrad", 1, 4.0 * dpad.numel(), L.ptr(dpre), L.ptr(w), L.ptr(dpad),
+             B, H, W, C, L.stream())
+    return dpad
 
 
 def head_wgrad(x, dpre, dw, dbias):
@@ -395,6 +404,7 @@ def spatial_mean_bwd(dout, x_shape, scale):
     return dx
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
-    L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, 28.0 * param.numel(), L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr, beta1,
-                                   beta2, eps, weight_decay, step, L.ptr(step_dev), L.stream())
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, step_dev=None, param_tf32=None):
+    L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, (32.0 if param_tf32 is not None else 28.0) * param.numel(), L.ptr(param),
+             L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, weight_decay, step, L.ptr(step_dev),
+             L.ptr(param_tf32), L.stream())

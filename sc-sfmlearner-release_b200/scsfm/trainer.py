@@ -36,6 +36,8 @@ class Trainer:
                  with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None):
         self.disp_net, self.pose_net = disp_net, pose_net
         self.optimizer = ArenaAdam([disp_net, pose_net], lr=lr, betas=betas, weight_decay=weight_decay)
+        for n in (disp_net, pose_net):
+            n.trust_adam_mirror = True      # this loop changes parameters only through ArenaAdam (which writes the TF32 mirror)
         self.cfg = dict(num_scales=num_scales, with_ssim=with_ssim, with_mask=with_mask, with_auto_mask=with_auto_mask,
                         padding_mode=padding_mode)
         self.w = (w1, w2, w3)
@@ -93,6 +95,10 @@ class Trainer:
             self._eager_step(*self._static)
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.restore(snap)
+        # restore() changed the parameters: bring the TF32 operand mirrors up to date NOW, so that the captured step contains
+        # no rounding pass (during replays the Adam kernel at the end of step k writes the mirror for step k+1)
+        for n in self.optimizer.nets:
+            n.refresh_operand_weights()
         # the warm-up step left the persistent flipped-weight buffers and their job tables in place: the capture below
         # records one batched refresh per network instead of one flip per layer
         before = L.launch_count()

@@ -111,3 +111,72 @@ def test_cuda_graph_replay_matches_eager_steps():
         np.testing.assert_allclose(b, a, rtol=2e-4 if it == 0 else 5e-3)
     assert graphed.optimizer.step_count == 3
     assert float((graphed.disp_net.flat_params() - eager.disp_net.flat_params()).abs().max()) <= 6.1e-4   # 3 steps x 2 lr
+
+
+def test_tf32_operand_mirror_and_batched_flips_stay_exact():
+    """tf32 mode shortcuts of the training loop: ArenaAdam writes the TF32-rounded operand copy of the parameters itself
+    (no rounding pass per network call) and all flipped data-gradient weights of a network are refreshed by ONE batched
+    launch.  Both must be bit-identical to the plain per-tensor kernels, eagerly and under CUDA-graph replay."""
+    import math
+    import models
+    from scsfm import nnops as O
+    from scsfm import synth
+    from scsfm.trainer import Trainer
+    tgt, refs, K = synth.triplet(3, 2, 96, 160)
+    args = (tgt.to(DEV), [r.to(DEV) for r in refs], K.to(DEV))
+
+    def make():
+        d, p = models.DispResNet(18, False), models.PoseResNet(18, False)
+        d.load_state_dict(det_weights(d.state_dict())); p.load_state_dict(det_weights(p.state_dict()))
+        return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False)
+
+    def mirror_in_sync(net):
+        want = torch.empty_like(net._flat)
+        O.round_tf32(net._flat, want)
+        return torch.equal(net._flat_tf32, want)
+
+    old = O.CONFIG["conv_mode"]
+    O.CONFIG["conv_mode"] = "tf32"
+    try:
+        O.invalidate_weight_cache()
+        tr = make()
+        for _ in range(3):                      # steps 2 and 3 run on the shortcuts
+            losses = tr.step(*args)
+        assert all(math.isfinite(float(v)) for v in losses)
+        nets = (tr.disp_net, tr.pose_net)
+        for net in nets:
+            assert net.trust_adam_mirror and net._tf32_version == net._versions()
+            assert mirror_in_sync(net)
+            net.refresh_operand_weights()       # batched flip refresh from the (current) mirror
+        cached = {k: v.clone() for k, v in O._flip_cache.items()}
+        assert len(cached) > 20
+        O.invalidate_weight_cache()
+        seen = 0
+        for net in nets:
+            lo = net._flat_tf32.data_ptr()
+            for key, got in cached.items():
+                ptr, shape, stride, pad = key
+                if not (lo <= ptr < lo + 4 * net._flat_tf32.numel()):
+                    continue
+                off = (ptr - lo) // 4
+                w = net._flat_tf32[off:off + math.prod(shape)].view(shape)
+                assert w.data_ptr() == ptr
+                assert torch.equal(O.flipped_weights(w, stride, pad), got), key
+                seen += 1
+        assert seen == len(cached)
+        # the same loop as one CUDA graph per step
+        O.invalidate_weight_cache()
+        gr = make()
+        gr.capture(*args)
+        for _ in range(2):
+            gr.step(*args)
+        torch.cuda.synchronize()
+        for net in (gr.disp_net, gr.pose_net):
+            assert mirror_in_sync(net)
+        # a parameter change the optimizer did not make must be noticed (torch version counters)
+        with torch.no_grad():
+            next(iter(gr.disp_net.parameters())).mul_(1.5)
+        assert gr.disp_net._tf32_version != gr.disp_net._versions()
+    finally:
+        O.CONFIG["conv_mode"] = old
+        O.invalidate_weight_cache()
