@@ -58,3 +58,40 @@ def test_host_side_helpers():
         loss_ops._padding("reflection")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         lib.dev_f32(torch.zeros(1, 3, 8, 8), "x")
+
+
+def test_network_entry_points_reject_bad_arguments_without_a_gpu():
+    """Host-side checks of the network operators added for the tensor-core path (no launch happens on an error)."""
+    from scsfm import lib
+    from scsfm import nnops as O
+    L = O._lib()
+    n0 = lib.launch_count()
+    assert L.scsfm_conv_tma_config(1, 3, 0, 0) == -1 and b"conv_tma_config" in L.scsfm_last_error()
+    assert L.scsfm_conv_tma_config(1, 0, 48, 0) == -1
+    assert L.scsfm_conv_tma_config(1, 0, 0, 5) == -1
+    assert L.scsfm_conv_tma_config(1, 2, 128, 4) == 0 and L.scsfm_conv_tma_config(1, 0, 0, 0) == 0
+    assert L.scsfm_weight_flip_batched(None, 1, 1, None) == -1
+    assert L.scsfm_head_conv_dgrad(None, None, None, 1, 8, 8, 16, None) == -1
+    assert L.scsfm_conv2d_fwd_tc(None, None) == -1
+    assert lib.launch_count() == n0          # nothing was launched
+
+
+def test_stride2_parity_classes_partition_the_taps():
+    """A stride-2 data gradient runs as four parity-class sub-convolutions: every tap of the kernel must belong to exactly
+    one class (the tap rows dy_max, dy_max-2, ... of class py are those with (py + pad - dy) even)."""
+    from scsfm import nnops as O
+    for k in (1, 3, 7):
+        for pad in (0, 1, 3):
+            classes = O._s2_classes(k, k, pad)
+            assert len(classes) == 4
+            owners = {}
+            for cls, (jh, jw, dy_max, dx_max) in enumerate(classes):
+                py, px = divmod(cls, 2)
+                for jy in range(jh):
+                    for jx in range(jw):
+                        dy, dx = dy_max - 2 * jy, dx_max - 2 * jx
+                        assert 0 <= dy < k and 0 <= dx < k
+                        assert (py + pad - dy) % 2 == 0 and (px + pad - dx) % 2 == 0
+                        assert (dy, dx) not in owners
+                        owners[(dy, dx)] = cls
+            assert len(owners) == k * k
