@@ -16,6 +16,8 @@
 // for reflection-padded layers it returns the gradient of the padded tensor (pad' = 2), folded afterwards.
 //
 // Replaces cuDNN implicit-GEMM fwd/dgrad for every layer with Cin % 4 == 0.
+#include <stdlib.h>
+
 #include "conv_tc.cuh"
 
 namespace scsfm {
@@ -473,6 +475,184 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t ra
     return fn(map, dtype, rank, gaddr, gdim, gstride, box, estr, il, sw, l2, oob);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// "wide" weight gradient (experimental, SCSFM_WGRAD_WIDE=1): the operand roles of the kernel above exchanged and the
+// (tap, channel) tile doubled.  A tcgen05.mma with both operands in shared memory costs ~140 cycles for M = 128 whatever
+// N is (measured on the forward kernel), so
+//     D[o (M = 128 lanes: output channels), (tap,c) (N = 256 columns)] += dout[pix, o]^T x gather(in)[pix, (tap,c)]
+// needs half the instructions of the M = (tap,c) / N = Cout arrangement for Cout = 128 and a quarter for Cout = 64.
+// Same MN-major BASE32B shared-memory layouts (atoms of 4 pixels x 32 channels, LBO = 512 B between atoms): the dout tile
+// always keeps four atoms per pixel group (M = 128; atoms beyond Cout hold stale shared memory and only feed unread
+// lanes), the gathered-input tile eight.  cp.async producers as above; the epilogue adds 16-byte vectors (red.v4.f32).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WW_N = 256;                                 // (tap, c) columns per CTA
+struct WwCfg {
+    static constexpr int STAGES = 2;
+    static constexpr int A_BYTES = 32 * WW_N * 4;         // 32 pixels x 256 (tap,c): 8 pixel groups x 8 atoms x 512 B
+    static constexpr int B_BYTES = 32 * TBM * 4;          // 32 pixels x 128 output channels (4 atoms, BN/32 of them loaded)
+    static constexpr int TMEM_COLS = WW_N;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>      // output channels actually loaded per pixel row: 32, 64 or 128
+__global__ void __launch_bounds__(FW_THREADS)
+conv_wgrad_wide_tc_kernel(ScsfmConv p, int pix_per_split) {
+    using Cfg = WwCfg;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                    // gathered input, N side
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;            // dout, M side
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+    uint64_t* bar_empty = bar_full + STAGES;
+    uint64_t* bar_acc = bar_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Mtot = p.kh * p.kw * p.Cin, N = p.Cout, npix = p.B * p.Ho * p.Wo;
+    const int m0 = blockIdx.x * WW_N, n0 = blockIdx.y * TBM;
+    const int pix_begin = blockIdx.z * pix_per_split, pix_end = min(npix, pix_begin + pix_per_split);
+    const int KB = (pix_end - pix_begin + 31) / 32;
+    if (KB <= 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(bar_full + s, FW_PWARPS * 32);
+            tc::mbar_init(bar_empty + s, 1);
+        }
+        tc::mbar_init(bar_acc, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < FW_PWARPS) {
+        // ------------------------------------------------------------------ producers
+        // A: 64 chunk columns (4 consecutive (tap,c) entries each, fixed per thread) x 32 pixels; thread = chunk column
+        // tid % 64 and the 8 consecutive pixels 8 * (tid / 64) .. + 7 of the k-block.
+        constexpr int PPT = 8;
+        const int cidx = tid & 63, kq = tid >> 6;
+        const int mm = m0 + 4 * cidx;
+        const bool a_ok = mm < Mtot;
+        int a_dy = 0, a_dx = 0, a_ch = 0;
+        if (a_ok) {
+            const int tap = mm / p.Cin;
+            a_ch = mm - tap * p.Cin;
+            a_dy = tap / p.kw - p.pad;
+            a_dx = tap - (tap / p.kw) * p.kw - p.pad;
+        }
+        const bool reflect = p.pad_mode == PADMODE_REFLECT;
+        const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)((cidx >> 3) * 512);       // atom = cidx / 8
+        const int a_chunk = cidx & 7;
+        // B: BN/4 chunks per pixel row
+        constexpr int BCH = BN / 4;
+        constexpr int B_IT = (32 * BCH) / (FW_PWARPS * 32);
+        constexpr int B_STEP = (FW_PWARPS * 32) / BCH;
+        const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
+        const int nn = n0 + 4 * b_c4;
+        const bool b_ok = nn < N;
+        const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)((b_c4 >> 3) * 512);
+        int pb, pho, pwo;
+        {
+            const int px = pix_begin + PPT * kq;
+            pb = px / (p.Ho * p.Wo);
+            const int rem = px - pb * p.Ho * p.Wo;
+            pho = rem / p.Wo;
+            pwo = rem - pho * p.Wo;
+        }
+        int pix0 = pix_begin;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
+            __syncwarp();
+            const uint32_t a_st = a_smem + (uint32_t)(s * Cfg::A_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_BYTES);
+            int b = pb, ho = pho, wo = pwo;
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                const int k = PPT * kq + i;                 // pixel row inside the block: group k/4, row k%4
+                const int px = pix0 + k;
+                int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
+                bool ok = a_ok && px < pix_end;
+                if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
+                else ok = ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                const int off = ok ? ((b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch : 0;
+                tc::cp_async_16(a_st + (k >> 2) * (8 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16),
+                                p.in + off, ok ? 16u : 0u);
+                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } }
+            }
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int k = b_kr0 + B_STEP * i;
+                const int px = pix0 + k;
+                const bool ok = b_ok && px < pix_end;
+                tc::cp_async_16(b_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
+                                p.dout + (ok ? (size_t)px * N + nn : 0), ok ? 16u : 0u);
+            }
+            tc::cp_async_arrive_noinc(bar_full + s);
+            pix0 += 32;
+            pwo += 32;
+            while (pwo >= p.Wo) { pwo -= p.Wo; if (++pho == p.Ho) { pho = 0; ++pb; } }
+        }
+
+        // ------------------------------------------------------------------ epilogue: dw[o][mm .. mm+3] += D[o][mm .. mm+3]
+        tc::mbar_wait(bar_acc, 0);
+        tc::fence_after_thread_sync();
+        const int quarter = warp & 3, half = warp >> 2;
+        const int o = n0 + quarter * 32 + lane;
+        if (n0 + quarter * 32 < N) {                      // warp-uniform: this lane quarter holds real output channels
+#pragma unroll 1
+            for (int cc = half; cc < WW_N / 32; cc += FW_PWARPS / 4) {
+                if (m0 + cc * 32 >= Mtot) break;
+                uint32_t r[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
+                tc::tmem_ld_wait();
+                if (o < N) {
+                    float* dst = p.dw + (size_t)o * Mtot + m0 + cc * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (m0 + cc * 32 + j < Mtot)       // Mtot % 4 == 0: a vector never straddles the end
+                            red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, WW_N, 1, 1);       // both operands MN-major
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(bar_full + s, ph);
+                tc::fence_proxy_async();
+                tc::fence_after_thread_sync();
+                const uint32_t a_addr = tc::smem_u32(sA + s * Cfg::A_BYTES);
+                const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {               // 4 x (2 pixel groups of 4): UMMA K = 8 for tf32
+                    // M side: dout, 4 atoms per pixel group (SBO = 4 * 512); N side: gathered input, 8 atoms (SBO = 8 * 512)
+                    const uint64_t dm = tc::make_smem_desc(b_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
+                    const uint64_t dn = tc::make_smem_desc(a_addr + j * (2 * 8 * 512), 512, 8 * 512, tc::LAYOUT_SW128_BASE32B);
+                    tc::mma_tf32(tmem_base, dm, dn, idesc, (kb | j) != 0 ? 1u : 0u);
+                }
+                tc::mma_commit(bar_empty + s);
+            }
+            tc::mma_commit(bar_acc);
+        }
+        __syncwarp();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
 
 template <int BN>
@@ -494,6 +674,36 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     conv_wgrad_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
+}
+
+template <int BN>
+static int launch_wgrad_wide_tc(const ScsfmConv& p, cudaStream_t st) {
+    using Cfg = WwCfg;
+    static bool configured = false;
+    if (!configured) {
+        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_wide_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * p.Ho * p.Wo;
+    const int mt = (Mtot + WW_N - 1) / WW_N, nt = (p.Cout + TBM - 1) / TBM;
+    int splits = (148 * 2 + mt * nt - 1) / (mt * nt);          // 2 CTAs per SM fit (96 KB of stages, 256 TMEM columns each)
+    const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
+    dim3 grid(mt, nt, (npix + pps - 1) / pps);
+    conv_wgrad_wide_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+static int g_wgrad_wide = -1;                   // -1: take SCSFM_WGRAD_WIDE from the environment on first use
+static int wgrad_wide_enabled() {               // experimental kernel, off unless SCSFM_WGRAD_WIDE=1 / scsfm_wgrad_config(1)
+    if (g_wgrad_wide < 0) {
+        const char* e = getenv("SCSFM_WGRAD_WIDE");
+        g_wgrad_wide = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return g_wgrad_wide;
 }
 
 static TcView plain_view(const ScsfmConv& p) {
@@ -728,6 +938,13 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
     return SCSFM_OK;
 }
 
+// experiment hook: 1 selects the wide (output channels on M, 256 (tap,c) columns on N) weight-gradient kernel, 0 the default
+extern "C" int scsfm_wgrad_config(int wide) {
+    SCSFM_CHECK_ARG(wide == 0 || wide == 1, "wgrad_config: bad arguments");
+    g_wgrad_wide = wide;
+    return SCSFM_OK;
+}
+
 // dw [Cout,kh,kw,Cin] += dout^T x gather(in); dbias += column sums of dout.  Needs Cin % 4 == 0 and Cout % 4 == 0.
 extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG(p != nullptr && p->in && p->dout && p->dw, "conv2d_wgrad_tc: null tensor");
@@ -738,7 +955,11 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG((long long)p->B * p->Ho * p->Wo < (1LL << 31), "conv2d_wgrad_tc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
+    if (wgrad_wide_enabled()) {
+        if (p->Cout <= 32) rc = launch_wgrad_wide_tc<32>(*p, st);
+        else if (p->Cout <= 64) rc = launch_wgrad_wide_tc<64>(*p, st);
+        else rc = launch_wgrad_wide_tc<128>(*p, st);
+    } else if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
     else if (p->Cout <= 64) rc = launch_wgrad_tc<64>(*p, st);
     else rc = launch_wgrad_tc<128>(*p, st);
     if (rc) return rc;

@@ -41,6 +41,7 @@ def _lib():
                 getattr(lib, name).argtypes = [CP, P]
         lib.scsfm_round_tf32.argtypes = [P, P, LL, P]
         lib.scsfm_conv_tma_config.argtypes = [I, I, I, I]
+        lib.scsfm_wgrad_config.argtypes = [I]
         if hasattr(lib, "scsfm_weight_flip"):
             lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
             lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, P]
@@ -71,6 +72,11 @@ def _lib():
 def conv_tma_config(enable=1, force_mt=0, force_bn=0, force_tw_log2=0):
     """Experiment hook of the TMA halo-patch convolution kernel (see include/scsfm.h)."""
     L.check(_lib().scsfm_conv_tma_config(enable, force_mt, force_bn, force_tw_log2), "scsfm_conv_tma_config")
+
+
+def wgrad_config(wide):
+    """Experiment hook: select the wide weight-gradient kernel (see include/scsfm.h)."""
+    L.check(_lib().scsfm_wgrad_config(int(wide)), "scsfm_wgrad_config")
 
 
 def rnd():
