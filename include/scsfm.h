@@ -188,8 +188,9 @@ int scsfm_conv_tma_config(int enable, int force_mt, int force_bn, int force_tw_l
 /* profiling hook: device array of 8 x (number of SMs) 64-bit cycle counters written by every later TMA-kernel launch
  * (producer / MMA-issuer / epilogue wait and total cycles per persistent CTA, see conv_tma.cu), NULL = off */
 int scsfm_conv_tma_debug(unsigned long long* buf);
-/* experiment hook: 1 = the "wide" weight-gradient kernel (output channels on the MMA's M side, 256 (tap, channel) columns on
- * the N side; not yet the default), 0 = the default kernel.  Environment: SCSFM_WGRAD_WIDE=1. */
+/* experiment hook: 0 = the default weight-gradient kernel; 1 = the "wide" one (output channels on the MMA's M side, 256
+ * (tap, channel) columns on the N side, cp.async producers: exact, not faster); 2 = the TMA one (conv_wgrad_tma.cu, stride-1
+ * zero-padded layers, NOT yet validated on a GPU).  Environment: SCSFM_WGRAD_WIDE=0|1|2. */
 int scsfm_wgrad_config(int wide);
 int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
 /* stride-2 data gradient: four parity-class weight sets back to back (Cin*kh*kw*Cout floats in total); p->w of

@@ -701,7 +701,7 @@ static int g_wgrad_wide = -1;                   // -1: take SCSFM_WGRAD_WIDE fro
 static int wgrad_wide_enabled() {               // experimental kernel, off unless SCSFM_WGRAD_WIDE=1 / scsfm_wgrad_config(1)
     if (g_wgrad_wide < 0) {
         const char* e = getenv("SCSFM_WGRAD_WIDE");
-        g_wgrad_wide = (e != nullptr && e[0] == '1') ? 1 : 0;
+        g_wgrad_wide = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
     }
     return g_wgrad_wide;
 }
@@ -938,9 +938,10 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
     return SCSFM_OK;
 }
 
-// experiment hook: 1 selects the wide (output channels on M, 256 (tap,c) columns on N) weight-gradient kernel, 0 the default
+// experiment hook: 0 the default kernel, 1 the wide one (output channels on M, 256 (tap,c) columns on N, cp.async
+// producers), 2 the TMA one (conv_wgrad_tma.cu; layers it does not take fall back to the default)
 extern "C" int scsfm_wgrad_config(int wide) {
-    SCSFM_CHECK_ARG(wide == 0 || wide == 1, "wgrad_config: bad arguments");
+    SCSFM_CHECK_ARG(wide >= 0 && wide <= 2, "wgrad_config: bad arguments");
     g_wgrad_wide = wide;
     return SCSFM_OK;
 }
@@ -955,7 +956,9 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG((long long)p->B * p->Ho * p->Wo < (1LL << 31), "conv2d_wgrad_tc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (wgrad_wide_enabled()) {
+    if (wgrad_wide_enabled() == 2 && conv_wgrad_tma_eligible(*p)) {
+        rc = launch_conv_wgrad_tma(*p, st);
+    } else if (wgrad_wide_enabled() == 1) {
         if (p->Cout <= 32) rc = launch_wgrad_wide_tc<32>(*p, st);
         else if (p->Cout <= 64) rc = launch_wgrad_wide_tc<64>(*p, st);
         else rc = launch_wgrad_wide_tc<128>(*p, st);

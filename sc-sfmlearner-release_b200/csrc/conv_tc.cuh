@@ -69,4 +69,8 @@ bool conv_tma_eligible(const ScsfmConv& p, const TcView& v);
 bool conv_tma_forced();      // a tile configuration is being forced through scsfm_conv_tma_config (tests / experiments)
 int launch_conv_tma(const ScsfmConv& p, const TcView& v, cudaStream_t st);
 
+// conv_wgrad_tma.cu (experimental): stride-1 zero-padded weight gradient with TMA-delivered operands
+bool conv_wgrad_tma_eligible(const ScsfmConv& p);
+int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st);
+
 }  // namespace scsfm

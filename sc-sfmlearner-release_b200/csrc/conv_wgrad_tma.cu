@@ -1,0 +1,244 @@
+// EXPERIMENTAL (scsfm_wgrad_config(2) / SCSFM_WGRAD_WIDE=2; not validated on a GPU yet, never selected by default):
+// weight gradient of a stride-1, zero-padded convolution with both operands delivered by TMA.
+//
+//   D[o (M = 128 TMEM lanes: output channels), (dy, chunk c, ch) (N = kh * G * 32 columns)] +=
+//        sum over the pixels p of a tile   dout[p, o] * in[p + (dy, dx) - pad, 32 * (G * cg + c) + ch]
+//
+// Measured in round 1 (profiles/r01b_wgrad_wide_check.txt): the cp.async weight-gradient kernels are bound by their 256
+// producer threads, not by the MMA count.  Here one thread issues TMA loads instead:
+//  * pixels are the K dimension and both operands are "MN-major" (channels contiguous), which for 32-bit types means the
+//    UMMA layout SWIZZLE_128B_BASE32B; CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B is its TMA twin (rows of 128 B = 32 channels of
+//    one pixel, 32-byte chunks XOR-swizzled with the pixel index mod 4);
+//  * a CTA owns one (Cout tile, group of G <= 2 channel chunks, dx) slice of dW and a range of pixel tiles (TH x TW = 128
+//    pixels of one image, TW in {8, 16}); per tile it loads the dout tile (one box per 32 output channels) and the input
+//    rows y0-pad .. y0-pad+TH+kh-2 shifted by dx, laid out [row][chunk][x][32 ch], so the (dy, chunk) operand atoms of the
+//    tile row r start at ((r + dy) * G + c) * TW * 128 bytes: one uniform stride TW*128 = the descriptor's LBO.  The kh
+//    vertical taps therefore share one load, as in conv_tma.cu;
+//  * one tcgen05.mma (K = 8 pixels) per 8-pixel slice of a tile row: 16 per tile, M = 128, N = kh*G*32 <= 192;
+//  * split-K over pixel-tile ranges (gridDim.z), fp32 vector red.add of the partial dW tiles.
+// Reflection-padded layers, stride 2 and kernels larger than 3x3 stay on the cp.async kernel.
+#include "conv_tc.cuh"
+
+namespace scsfm {
+
+constexpr int WT_EWARPS = 8;
+constexpr int WT_THREADS = (WT_EWARPS + 2) * 32;
+constexpr int WT_MAX_STAGES = 4;
+constexpr int WT_DOUT_BYTES = 4 * TBM * 128;        // four 32-channel atoms x 128 pixels x 128 B (atoms beyond Cout stay stale)
+constexpr int WT_SMEM_MAX = 232448;
+
+struct WtGeom {
+    int tw_log2;                 // TW = 1 << tw_log2 (3 or 4), TH = 128 >> tw_log2
+    int tiles_x, tiles_y;        // pixel tiles per image
+    int tiles_total;             // B * tiles_y * tiles_x
+    int tiles_per_split;
+    int groups, G;               // channel-chunk groups of G chunks (the last group may hold fewer real chunks)
+    int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4)
+    int stages, patch_bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dmap) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar_empty = bar_full + WT_MAX_STAGES;
+    uint64_t* bar_acc = bar_empty + WT_MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+    uint8_t* ring = smem + 1024;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
+    const int cg = blockIdx.x / p.kw, dx = blockIdx.x - cg * p.kw;        // channel-chunk group, horizontal tap
+    const int n0 = blockIdx.y * TBM;                                     // first output channel of this CTA
+    const int t_begin = blockIdx.z * g.tiles_per_split, t_end = min(g.tiles_total, t_begin + g.tiles_per_split);
+    const int ntiles = t_end - t_begin;
+    if (ntiles <= 0) return;
+    const int chunk0 = cg * g.G;                                         // first 32-channel chunk of the group
+    const int natoms = p.kh * g.G;                                       // N atoms of the accumulator
+    const int NCOLS = natoms * 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            tc::mbar_init(bar_full + s, 1);
+            tc::mbar_init(bar_empty + s, 1);
+        }
+        tc::mbar_init(bar_acc, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == WT_EWARPS + 1) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t ring_base = tc::smem_u32(ring);
+
+    if (warp == WT_EWARPS) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            tc::tma_prefetch_desc(&xmap);
+            tc::tma_prefetch_desc(&dmap);
+            const int prows = TH + p.kh - 1;
+            const uint32_t row_bytes = (uint32_t)(TW * 128);
+            const uint32_t tx_bytes = (uint32_t)(g.atoms_m * TBM * 128) + (uint32_t)(prows * g.G) * row_bytes;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                int q = t;
+                const int tx = q % g.tiles_x; q /= g.tiles_x;
+                const int ty = q % g.tiles_y;
+                const int b = q / g.tiles_y;
+                const int y0 = ty * TH, x0 = tx * TW;
+                tc::mbar_wait(bar_empty + s, ph ^ 1);
+                const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
+                tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
+                // M side: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
+                for (int a = 0; a < g.atoms_m; ++a)
+                    tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
+                // N side: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
+                const uint32_t pst = st + WT_DOUT_BYTES;
+                for (int r = 0; r < prows; ++r)
+                    for (int c = 0; c < g.G; ++c)
+                        tc::tma_load_4d(pst + (uint32_t)(r * g.G + c) * row_bytes, &xmap, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
+                                        bar_full + s);
+                if (++s == g.stages) { s = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == WT_EWARPS + 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(TBM, NCOLS, 1, 1);               // both operands MN-major
+            // constant descriptor fields; the start address (>> 4) is added per MMA
+            const uint64_t dm0 = tc::make_smem_desc(0, TBM * 128, 512, tc::LAYOUT_SW128_BASE32B);            // atoms 16 KB apart
+            const uint64_t dn0 = tc::make_smem_desc(0, (uint32_t)(TW * 128), 512, tc::LAYOUT_SW128_BASE32B);   // atoms one (row, chunk) block apart
+            const int slices = TW >> 3;                       // 8-pixel slices per tile row
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                tc::mbar_wait(bar_full + s, ph);
+                tc::fence_after_thread_sync();
+                const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
+                const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
+                for (int r = 0; r < TH; ++r) {
+                    for (int kq = 0; kq < slices; ++kq) {
+                        const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
+                        const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
+                        tc::mma_tf32(tmem_base, dm, dn, idesc, (t != t_begin || r != 0 || kq != 0) ? 1u : 0u);
+                    }
+                }
+                tc::mma_commit(bar_empty + s);
+                if (++s == g.stages) { s = 0; ph ^= 1; }
+            }
+            tc::mma_commit(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue: dw[o][(dy, dx, channel)] += D[o][...]
+        tc::mbar_wait(bar_acc, 0);
+        tc::fence_after_thread_sync();
+        const int quarter = warp & 3, half = warp >> 2;
+        const int o = n0 + quarter * 32 + lane;
+        const int Mtot = p.kh * p.kw * p.Cin;
+        if (n0 + quarter * 32 < p.Cout) {                 // warp-uniform: this lane quarter holds real output channels
+#pragma unroll 1
+            for (int a = half; a < natoms; a += WT_EWARPS / 4) {
+                const int dy = a / g.G, c = a - dy * g.G;
+                const int ch0 = 32 * (chunk0 + c);            // first input channel of this atom
+                if (ch0 >= p.Cin) continue;                   // padding chunk of the last group
+                uint32_t r[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 32), r);
+                tc::tmem_ld_wait();
+                if (o < p.Cout) {
+                    float* dst = p.dw + (size_t)o * Mtot + (size_t)(dy * p.kw + dx) * p.Cin + ch0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (ch0 + j < p.Cin)                  // Cin % 4 == 0: a vector never straddles the end
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                                         : "memory");
+                }
+            }
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == WT_EWARPS + 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
+bool conv_wgrad_tma_eligible(const ScsfmConv& p) {
+    return p.stride == 1 && p.pad_mode == PADMODE_ZERO && p.kh >= 1 && p.kh <= 3 && p.kw >= 1 && p.kw <= 3 && (p.Cin & 3) == 0 &&
+           (p.Cout & 3) == 0 && p.Ho == p.Hi + 2 * p.pad - p.kh + 1 && p.Wo == p.Wi + 2 * p.pad - p.kw + 1;
+}
+
+int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX));
+        configured = true;
+    }
+    WtGeom g;
+    // tile shape: least padded area
+    const long a16 = (long)((p.Ho + 7) / 8 * 8) * ((p.Wo + 15) / 16 * 16), a8 = (long)((p.Ho + 15) / 16 * 16) * ((p.Wo + 7) / 8 * 8);
+    g.tw_log2 = a8 < a16 ? 3 : 4;
+    const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
+    g.tiles_x = (p.Wo + TW - 1) / TW;
+    g.tiles_y = (p.Ho + TH - 1) / TH;
+    g.tiles_total = g.tiles_x * g.tiles_y * p.B;
+    const int chunks = (p.Cin + 31) / 32;
+    g.G = chunks >= 2 ? 2 : 1;
+    g.groups = (chunks + g.G - 1) / g.G;
+    const int nt = (p.Cout + TBM - 1) / TBM;
+    const int cout_tile = p.Cout < TBM ? p.Cout : TBM;             // (the last Cout tile may need fewer atoms; extra rows are zero-filled)
+    g.atoms_m = (cout_tile + 31) / 32;
+    g.patch_bytes = (TH + p.kh - 1) * g.G * TW * 128;
+    g.stage_bytes = WT_DOUT_BYTES + (g.patch_bytes + 1023) / 1024 * 1024;
+    g.stages = (WT_SMEM_MAX - 2048) / g.stage_bytes;
+    if (g.stages > WT_MAX_STAGES) g.stages = WT_MAX_STAGES;
+    if (g.stages < 2) {
+        set_error("conv_wgrad_tma: stage of %d bytes does not fit twice in shared memory", g.stage_bytes);
+        return SCSFM_ERR_ARG;
+    }
+    // split the pixel tiles so that about two waves of CTAs exist, with at least 8 tiles per CTA
+    const int slices = g.groups * p.kw * nt;
+    int splits = (2 * 148 + slices - 1) / slices;
+    const int max_splits = (g.tiles_total + 7) / 8;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    g.tiles_per_split = (g.tiles_total + splits - 1) / splits;
+    splits = (g.tiles_total + g.tiles_per_split - 1) / g.tiles_per_split;
+    CUtensorMap xmap, dmap;
+    {
+        const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.B};
+        const cuuint64_t gstride[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Wi * p.Cin * 4, (cuuint64_t)p.Hi * p.Wi * p.Cin * 4};
+        const cuuint32_t box[4] = {32, (cuuint32_t)TW, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = encode_tiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(wgrad input %d x %d x %d x %d) failed with CUresult %d", p.B, p.Hi, p.Wi, p.Cin, (int)r);
+            return SCSFM_ERR_CUDA;
+        }
+    }
+    {
+        const cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
+        const cuuint64_t gstride[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.Wo * p.Cout * 4, (cuuint64_t)p.Ho * p.Wo * p.Cout * 4};
+        const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = encode_tiled(&dmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.dout), gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(wgrad dout %d x %d x %d x %d) failed with CUresult %d", p.B, p.Ho, p.Wo, p.Cout, (int)r);
+            return SCSFM_ERR_CUDA;
+        }
+    }
+    const size_t smem = 2048 + (size_t)g.stages * g.stage_bytes;
+    dim3 grid(g.groups * p.kw, nt, splits);
+    conv_wgrad_tma_kernel<<<grid, WT_THREADS, smem, st>>>(p, g, xmap, dmap);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
+}  // namespace scsfm

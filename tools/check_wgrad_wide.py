@@ -1,7 +1,8 @@
-"""Correctness + timing of the experimental wide weight-gradient kernel (scsfm_wgrad_config(1)) against the default
-tcgen05 wgrad kernel and an fp64 torch reference, over the layer shapes of DispResNet18 / PoseResNet18 at 256x832.
+"""Correctness + timing of the experimental weight-gradient kernels (scsfm_wgrad_config(1): wide cp.async kernel,
+scsfm_wgrad_config(2): TMA kernel) against the default tcgen05 wgrad kernel and an fp64 torch reference, over the layer
+shapes of DispResNet18 / PoseResNet18 at 256x832.
 
-Usage: python tools/check_wgrad_wide.py
+Usage: python tools/check_wgrad_wide.py [mode]      (mode 1 or 2, default 1)
 """
 import os
 import sys
@@ -16,6 +17,9 @@ from scsfm import nnops as O
 O.CONFIG["conv_mode"] = "tf32"
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+
+
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 
 
 def tf32(x):
@@ -84,13 +88,13 @@ for (name, B, H, W, Cin, Cout, k, s, pad, reflect) in CASES:
 
     dw0, db0 = run(0)
     t0 = timeit(lambda: run(0))
-    dw1, db1 = run(1)
+    dw1, db1 = run(MODE)
     torch.cuda.synchronize()
-    t1 = timeit(lambda: run(1))
+    t1 = timeit(lambda: run(MODE))
     e0, e1, d = rel(dw0, ref), rel(dw1, ref), rel(dw1, dw0)
     ok = e1 < 2e-3 and d < 1e-4 and rel(db1, rb) < 1e-4
     bad += 0 if ok else 1
-    print("%-12s B%-2d %3dx%-3d C%3d->%-3d k%d s%d | err ref %.1e %.1e | wide-vs-default %.1e | %7.3f -> %7.3f ms  x%.2f %s"
+    print("%-12s B%-2d %3dx%-3d C%3d->%-3d k%d s%d | err ref %.1e %.1e | mode-vs-default %.1e | %7.3f -> %7.3f ms  x%.2f %s"
           % (name, B, H, W, Cin, Cout, k, s, e0, e1, d, t0, t1, t0 / t1, "" if ok else "  <-- MISMATCH"), flush=True)
 O.wgrad_config(0)
 print("MISMATCHES: %d" % bad)
