@@ -303,7 +303,10 @@ struct WgCfg {
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
-template <int BN>
+// BORDER = true (used after the zero-padding TMA weight-gradient kernel on a reflection-padded layer): the K dimension only
+// runs over the 2*(Ho+Wo)-4 border pixels of every image and only the taps that fall OUTSIDE the image contribute, read
+// at their reflected positions -- exactly the part of the gradient the zero-padded pass left out.
+template <int BN, bool BORDER = false>
 __global__ void __launch_bounds__(FW_THREADS)
 conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     using Cfg = WgCfg<BN>;
@@ -318,7 +321,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Mtot = p.kh * p.kw * p.Cin, N = p.Cout, npix = p.B * p.Ho * p.Wo;
+    const int nb = BORDER ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo;        // K pixels per image
+    const int Mtot = p.kh * p.kw * p.Cin, N = p.Cout, npix = p.B * nb;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
     const int pix_begin = blockIdx.z * pix_per_split, pix_end = min(npix, pix_begin + pix_per_split);
     const int KB = (pix_end - pix_begin + 31) / 32;
@@ -387,22 +391,37 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
             for (int i = 0; i < PPT; ++i) {
                 const int k = PPT * kq + i;                 // pixel row inside the block: group k/4, row k%4
                 const int px = pix0 + k;
-                int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
                 bool ok = a_ok && px < pix_end;
-                if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
+                if (BORDER) {
+                    // k-th border pixel of the block; only taps leaving the image count, at their mirrored position
+                    b = px / nb;
+                    border_pixel(px - b * nb, p.Ho, p.Wo, ho, wo);
+                }
+                int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
+                if (BORDER) {
+                    ok = ok && !((unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi);
+                    hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi);
+                } else if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
                 else ok = ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
                 const int off = ok ? ((b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch : 0;
                 tc::cp_async_16(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16),
                                 p.in + off, ok ? 16u : 0u);
-                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } }
+                if (!BORDER) { if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } } }
             }
 #pragma unroll
             for (int i = 0; i < B_IT; ++i) {
                 const int k = b_kr0 + B_STEP * i;
                 const int px = pix0 + k;
                 const bool ok = b_ok && px < pix_end;
+                size_t row = (size_t)px;                       // row of dout
+                if (BORDER && ok) {
+                    const int bb = px / nb;
+                    int bho, bwo;
+                    border_pixel(px - bb * nb, p.Ho, p.Wo, bho, bwo);
+                    row = ((size_t)bb * p.Ho + bho) * p.Wo + bwo;
+                }
                 tc::cp_async_16(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
-                                p.dout + (ok ? (size_t)px * N + nn : 0), ok ? 16u : 0u);
+                                p.dout + (ok ? row * N + nn : 0), ok ? 16u : 0u);
             }
             tc::cp_async_arrive_noinc(bar_full + s);
             pix0 += 32;
@@ -655,15 +674,15 @@ conv_wgrad_wide_tc_kernel(ScsfmConv p, int pix_per_split) {
 
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
 
-template <int BN>
+template <int BN, bool BORDER = false>
 static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     using Cfg = WgCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
-    const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * p.Ho * p.Wo;
+    const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * (BORDER ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     const int mt = (Mtot + TBM - 1) / TBM, nt = (p.Cout + BN - 1) / BN;
     int splits = (148 * 3 + mt * nt - 1) / (mt * nt);          // 3 CTAs per SM fit
     const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
@@ -671,7 +690,7 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     if (splits < 1) splits = 1;
     const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
     dim3 grid(mt, nt, (npix + pps - 1) / pps);
-    conv_wgrad_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
+    conv_wgrad_tc_kernel<BN, BORDER><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -956,8 +975,19 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG((long long)p->B * p->Ho * p->Wo < (1LL << 31), "conv2d_wgrad_tc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (wgrad_wide_enabled() == 2 && conv_wgrad_tma_eligible(*p)) {
+    ScsfmConv zp = *p;                         // the same layer with zero padding (what the TMA kernel computes)
+    zp.pad_mode = SCSFM_PADMODE_ZERO;
+    if (wgrad_wide_enabled() == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
+    } else if (wgrad_wide_enabled() == 2 && p->pad_mode == PADMODE_REFLECT && p->pad == 1 && p->Ho >= 3 && p->Wo >= 3 &&
+               p->Ho * p->Wo >= 64 * 208 && conv_wgrad_tma_eligible(zp)) {
+        // reflection padding: zero-padded pass + the contributions of the taps that leave the image (border pixels only)
+        rc = launch_conv_wgrad_tma(zp, st);
+        if (rc == SCSFM_OK) {
+            if (p->Cout <= 32) rc = launch_wgrad_tc<32, true>(*p, st);
+            else if (p->Cout <= 64) rc = launch_wgrad_tc<64, true>(*p, st);
+            else rc = launch_wgrad_tc<128, true>(*p, st);
+        }
     } else if (wgrad_wide_enabled() == 1) {
         if (p->Cout <= 32) rc = launch_wgrad_wide_tc<32>(*p, st);
         else if (p->Cout <= 64) rc = launch_wgrad_wide_tc<64>(*p, st);
