@@ -167,6 +167,13 @@ def run_ours(args):
     graphed = world == 1 and not args.no_graph
     if graphed:
         trainer.capture(d_tgt, d_refs, d_K)
+    elif world > 1 and args.graph_ddp:
+        # opt-in experiment: the data-parallel step (incl. the NCCL all-reduce on the side stream) as one CUDA graph
+        try:
+            trainer.capture(d_tgt, d_refs, d_K, allow_distributed=True)
+            graphed = True
+        except Exception as e:      # noqa: BLE001 -- fall back to the validated eager path
+            print("graph capture of the data-parallel step failed, running eagerly: %r" % (e,), file=sys.stderr)
     launches0 = L.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -353,6 +360,7 @@ def main():
     ap.add_argument("--conv-mode", choices=["fp32", "tf32"], default="tf32",
                     help="tf32 = tcgen05 tensor-core convolutions (the reference's own cuDNN default arithmetic on a GPU); fp32 = exact CUDA-core parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-ddp", action="store_true", help="N>1: try to capture the data-parallel step in a CUDA graph (experimental)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -78,13 +78,14 @@ class Trainer:
             return tuple(self._static_out.unbind(0))
         return self._eager_step(tgt_img, ref_imgs, intrinsics)
 
-    def capture(self, tgt_img, ref_imgs, intrinsics):
+    def capture(self, tgt_img, ref_imgs, intrinsics, allow_distributed=False):
         """Record the whole step (7 network calls forward + backward, losses, Adam) into one CUDA graph: ~2500
         kernel launches become a single graph launch.  One eager warm-up step runs first (lazy allocations,
         Adam state) and is undone, so capturing does not advance training.  Single-GPU path."""
         from . import lib as L
-        if self.exchange is not None:
-            raise RuntimeError("graph capture of the data-parallel step is not enabled")
+        if self.exchange is not None and not allow_distributed:
+            raise RuntimeError("graph capture of the data-parallel step is opt-in (allow_distributed=True): capturing the NCCL "
+                               "all-reduce on the side stream has not been validated on this pod yet")
         self._static = (tgt_img.clone(), [r.clone() for r in ref_imgs], intrinsics.clone())
         snap = self.optimizer.snapshot()
         prof = dict(L.PROF)
@@ -103,7 +104,10 @@ class Trainer:
         # records one batched refresh per network instead of one flip per layer
         before = L.launch_count()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # with the gradient exchange the capture also records the NCCL all-reduces issued on the side stream (joined through
+        # events); NCCL's watchdog thread may touch CUDA meanwhile, hence the thread-local capture mode
+        mode = "thread_local" if self.exchange is not None else "global"
+        with torch.cuda.graph(graph, capture_error_mode=mode):
             self._static_out = torch.stack(self._eager_step(*self._static))
         self.launches_per_step = L.launch_count() - before
         self._graph = graph
