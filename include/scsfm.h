@@ -165,7 +165,27 @@ typedef struct ScsfmConv {
     double* bn_sums;
     int bn_groups;
     int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, pad_mode, act;
+    /* Split-accumulate ("3xTF32") operands of the tensor-core entry points, each optional (NULL = plain TF32):
+     * X_lo = tf32(X - trunc_tf32(X)) of the matching tensor (scsfm_split_tf32).  kind::tf32 reads only the upper 19 bits
+     * of an fp32 operand, so the raw tensor IS the high part; with the low parts given the kernel accumulates
+     * hi*hi + lo*hi + hi*lo into the same TMEM accumulator (the dropped lo*lo term is 2^-22 relative), which restores
+     * fp32-level accuracy of the products (cuDNN's/torch's "highest" matmul precision on the same hardware).
+     *   fwd:   in_lo, w_lo      dgrad: dout_lo, w_lo (flipped like w)      wgrad: in_lo, dout_lo */
+    const float* in_lo;
+    const float* w_lo;
+    const float* dout_lo;
+    /* per-call experiment knobs (0 = the heuristics) and per-call profiling buffer: nothing in the library is
+     * process-global mutable state */
+    unsigned tune;
+    unsigned long long* debug;   /* device array of 8 x (number of SMs) cycle counters written by the TMA conv kernel, or NULL */
 } ScsfmConv;
+
+/* ScsfmConv.tune */
+#define SCSFM_TUNE_NO_TMA 0x1u                          /* fwd/dgrad: cp.async gather kernel only */
+#define SCSFM_TUNE_MT(mt) (((unsigned)(mt) & 3u) << 4)       /* TMA kernel: 1|2 stacked 128-pixel sub-tiles (0 = auto) */
+#define SCSFM_TUNE_TW(l2) (((unsigned)((l2) ? (l2) - 2 : 0) & 3u) << 6)   /* TMA kernel: tile width log2 3|4 (0 = auto) */
+#define SCSFM_TUNE_BN(bn) (((bn) == 16 ? 1u : (bn) == 32 ? 2u : (bn) == 64 ? 3u : (bn) == 128 ? 4u : 0u) << 8)  /* weight rows in smem */
+#define SCSFM_TUNE_WGRAD(k) (((unsigned)(k) & 3u) << 12)     /* weight gradient: 0 auto, 1 cp.async kernel, 2 TMA kernel */
 
 /* Exact-fp32 implicit-GEMM convolution on CUDA cores (every shape). */
 int scsfm_conv2d_fwd_simt(const ScsfmConv* p, void* stream);
@@ -182,23 +202,18 @@ int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream);
 int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream);
-/* test / experiment hook: enable = 0 routes every layer through the gather kernel; force_mt (1|2 stacked 128-pixel
- * sub-tiles), force_bn (16|32|64|128), force_tw_log2 (3|4) override the tile heuristic, 0 = automatic */
-int scsfm_conv_tma_config(int enable, int force_mt, int force_bn, int force_tw_log2);
-/* profiling hook: device array of 8 x (number of SMs) 64-bit cycle counters written by every later TMA-kernel launch
- * (producer / MMA-issuer / epilogue wait and total cycles per persistent CTA, see conv_tma.cu), NULL = off */
-int scsfm_conv_tma_debug(unsigned long long* buf);
-/* experiment hook: 0 = the default weight-gradient kernel; 1 = the "wide" one (output channels on the MMA's M side, 256
- * (tap, channel) columns on the N side, cp.async producers: exact, not faster); 2 = the TMA one (conv_wgrad_tma.cu, stride-1
- * zero-padded layers, NOT yet validated on a GPU).  Environment: SCSFM_WGRAD_WIDE=0|1|2. */
-int scsfm_wgrad_config(int wide);
-int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream);
+/* Operand copies of a tensor for the tensor-core kernels: */
+#define SCSFM_OPERAND_TF32 0     /* round-to-nearest TF32 (plain TF32 mode) */
+#define SCSFM_OPERAND_RAW 1      /* bits unchanged (split mode: the MMA truncates, i.e. reads the high part) */
+#define SCSFM_OPERAND_LO 2       /* tf32(x - trunc_tf32(x)) (split mode: the low part) */
+/* flipped / transposed weights of the data gradient, `operand` = one of the above */
+int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, int operand, void* stream);
 /* stride-2 data gradient: four parity-class weight sets back to back (Cin*kh*kw*Cout floats in total); p->w of
  * scsfm_conv2d_dgrad_tc must point to them when p->stride == 2 */
-int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream);
+int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, int operand, void* stream);
 
 /* Every flip of a network in one launch (the weights change once per optimizer step).  table: device array of
- * (n_rows + 1) x 12 int64 {src pointer, dst pointer, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, tap step, first block};
+ * (n_rows + 1) x 12 int64 {src pointer, dst pointer, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, tap step | operand << 8, first block};
  * one row per scsfm_weight_flip job / per stride-2 parity class with taps (jh x jw taps kept, starting at (dy_max, dx_max)
  * and walking backwards by `tap step`); a row owns ceil(Cout/32) * ceil(Cin/32) * jh * jw blocks (one 32 x 32 tile
  * of one tap each) starting at its first block; the last row is a sentinel whose first block is total_blocks. */
@@ -213,10 +228,10 @@ int scsfm_head_conv_dgrad(const float* dpre, const float* w, float* dpad, int B,
 
 /* [B,C,H,W] (x1 or x2 sources, PoseResNet.py:65 torch.cat) -> NHWC [B,H,W,C*nsrc] */
 int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, int H, int W, float* out, void* stream);
-/* same with the channel count zero-padded to Cpad and values rounded to TF32 (7x7 stems on the tensor cores: 3 -> 4, 6 -> 8) */
-int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, void* stream);
-/* rows of C floats -> rows of Cpad floats (zero padded, TF32 rounded) and the inverse accumulation dst[r][c] += src[r][c] */
-int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, void* stream);
+/* same with the channel count zero-padded to Cpad (7x7 stems on the tensor cores: 3 -> 4, 6 -> 8); operand = SCSFM_OPERAND_* */
+int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, int operand, void* stream);
+/* rows of C floats -> rows of Cpad floats (zero padded, operand = SCSFM_OPERAND_*) and the inverse accumulation dst[r][c] += src[r][c] */
+int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, int operand, void* stream);
 int scsfm_unpad_add(const float* src, long long rows, int C, int Cpad, float* dst, void* stream);
 /* NHWC [B,H,W,C] -> NCHW */
 int scsfm_nhwc_to_nchw(const float* in, int B, int C, int H, int W, float* out, void* stream);
@@ -263,13 +278,16 @@ int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale,
 
 /* out[i] = round-to-nearest TF32 of in[i] (weights of the tensor-core convolutions, once per optimizer step) */
 int scsfm_round_tf32(const float* in, float* out, long long n, void* stream);
+/* lo[i] = tf32(in[i] - trunc_tf32(in[i])): the low part of the split-accumulate operands (ScsfmConv.in_lo / w_lo / dout_lo) */
+int scsfm_split_tf32(const float* in, float* lo, long long n, void* stream);
 
 /* Adam (torch.optim.Adam semantics, train.py:176-178) over a flat parameter arena.  The 1-based step count is
  * `step`, or *step_dev (device int) when step_dev != NULL so that a captured CUDA graph stays valid.
- * param_tf32 (optional): receives the updated parameters rounded to TF32 (the tensor-core convolutions' operand copy). */
+ * mirror (optional): receives the tensor-core operand copy of the updated parameters, mirror_operand = SCSFM_OPERAND_TF32
+ * (rounded, plain TF32 mode) or SCSFM_OPERAND_LO (low part, split mode). */
 int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                    float* param_tf32, void* stream);
+                    float* mirror, int mirror_operand, void* stream);
 
 #ifdef __cplusplus
 }

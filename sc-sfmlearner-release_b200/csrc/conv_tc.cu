@@ -24,7 +24,7 @@ namespace scsfm {
 
 template <int BN>
 __global__ void __launch_bounds__(FW_THREADS)
-conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wmap) {
+conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap wmap_lo) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -41,6 +41,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
     const int M = p.B * rows_per_img, N = p.Cout, K = v.kh * v.kw * p.Cin;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
     const int KB = (K + TBK - 1) / TBK;
+    // split-accumulate passes over the whole K range (ScsfmConv.in_lo / w_lo): raw x raw, lo(in) x raw(w), raw(in) x lo(w)
+    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.w_lo != nullptr ? 1 : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -50,6 +52,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         tc::mbar_init(bar_acc, 1);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&wmap);
+        if (p.w_lo != nullptr) tc::tma_prefetch_desc(&wmap_lo);
     }
     if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc::fence_before_thread_sync();
@@ -87,14 +90,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         }
         const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)(r0 * 128 + cs * 16);
         const uint32_t b_smem = tc::smem_u32(sB);
-        int kc = 4 * c;
-        int dy, dx, ch;
-        {
-            const int tap = kc / p.Cin;
-            ch = kc - tap * p.Cin;
-            dy = tap / v.kw;
-            dx = tap - dy * v.kw;
-        }
+        int kc, dy, dx, ch;
         // Asynchronous copies (cp.async / LDGSTS, 16 B, zero-fill for out-of-image taps): no register staging, so the
         // loads of all pipeline stages are in flight at once; the stage's "full" mbarrier gets this thread's arrival
         // when its copies have landed (cp.async.mbarrier.arrive.noinc).  The MMA thread issues fence.proxy.async after
@@ -102,10 +98,21 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         // Row offsets / validity only change with the tap, i.e. every Cin/32 k-blocks: they are cached in between.
         int aoff[ROWS];
         uint32_t okm = 0;
+        int it = 0;                                  // k-block counter across the passes: stage = it % STAGES
+        for (int ps = 0; ps < npass; ++ps) {
+        const float* a_base = (ps == 1 && p.in_lo != nullptr) ? p.in_lo : p.in;
+        const CUtensorMap* wm = (ps == npass - 1 && ps > 0 && p.w_lo != nullptr) ? &wmap_lo : &wmap;
+        kc = 4 * c;
+        {
+            const int tap = kc / p.Cin;
+            ch = kc - tap * p.Cin;
+            dy = tap / v.kw;
+            dx = tap - dy * v.kw;
+        }
         int cur_dy = -1, cur_dx = -1;
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
             if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
             __syncwarp();
             const uint32_t a_st = a_smem + (uint32_t)(s * A_STAGE_BYTES);
@@ -113,7 +120,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                 // weights: TMA box (32 K-columns x BN rows) straight into the 128B-swizzled stage; rows / columns beyond
                 // Cout / K are zero-filled by the hardware and still count towards the expected bytes
                 tc::mbar_arrive_expect_tx(bar_full + s, (uint32_t)Cfg::B_STAGE_BYTES);
-                tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), &wmap, kb * TBK, n0, bar_full + s);
+                tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), wm, kb * TBK, n0, bar_full + s);
             }
             if (dy != cur_dy || dx != cur_dx) {
                 cur_dy = dy; cur_dx = dx;
@@ -137,7 +144,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) {
                 const bool ok = kok && ((okm >> i) & 1u);
-                tc::cp_async_16(a_st + i * 4096, p.in + (ok ? aoff[i] + ch : 0), ok ? 16u : 0u);
+                tc::cp_async_16(a_st + i * 4096, a_base + (ok ? aoff[i] + ch : 0), ok ? 16u : 0u);
             }
             tc::cp_async_arrive_noinc(bar_full + s);
             // advance this thread's K index by one k-block
@@ -147,6 +154,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                 ch -= p.Cin;
                 if (++dx == v.kw) { dx = 0; ++dy; }
             }
+        }
         }
 
         // ------------------------------------------------------------------ epilogue (same 4 warps)
@@ -241,7 +249,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         // ------------------------------------------------------------------ MMA issuer (warp 4)
         constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 0, 0);
         if (lane == 0) {                                 // one thread waits, issues and commits
-            for (int kb = 0; kb < KB; ++kb) {
+            for (int kb = 0; kb < KB * npass; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 tc::mbar_wait(bar_full + s, ph);
@@ -271,7 +279,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
 // the (TF32-rounded) weights of the transposed conv.  step 1, d*_max = k-1: the full flipped kernel (stride-1 dgrad);
 // step 2: the taps of one output-parity class of a stride-2 dgrad.
 __global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int kh, int kw, int Ci, int jh, int jw, int dy_max,
-                                   int dx_max, int step, float* __restrict__ wt) {
+                                   int dx_max, int step, float* __restrict__ wt, int operand) {
     const long long total = (long long)Co * jh * jw * Ci;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int o = (int)(i % Co);
@@ -280,7 +288,7 @@ __global__ void weight_flip_kernel(const float* __restrict__ w, int Co, int kh, 
         const int jy = (int)(t2 % jh);
         const int c = (int)(t2 / jh);
         const int dy = dy_max - step * jy, dx = dx_max - step * jx;
-        wt[i] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
+        wt[i] = tc_operand(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c), operand);
     }
 }
 
@@ -327,6 +335,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     const int pix_begin = blockIdx.z * pix_per_split, pix_end = min(npix, pix_begin + pix_per_split);
     const int KB = (pix_end - pix_begin + 31) / 32;
     if (KB <= 0) return;
+    // split-accumulate passes over the CTA's pixel range (ScsfmConv.in_lo / dout_lo): raw x raw, lo(in) x raw(dout), raw(in) x lo(dout)
+    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -372,6 +382,10 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)((b_c4 >> 3) * 512);
         // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
         int pb, pho, pwo;
+        int it = 0;                                  // k-block counter across the passes: stage = it % STAGES
+        for (int ps = 0; ps < npass; ++ps) {
+        const float* a_base = (ps == 1 && p.in_lo != nullptr) ? p.in_lo : p.in;
+        const float* b_base = (ps == npass - 1 && ps > 0 && p.dout_lo != nullptr) ? p.dout_lo : p.dout;
         {
             const int px = pix_begin + PPT * kq;
             pb = px / (p.Ho * p.Wo);
@@ -380,9 +394,9 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
             pwo = rem - pho * p.Wo;
         }
         int pix0 = pix_begin;
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
             if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
             __syncwarp();
             const uint32_t a_st = a_smem + (uint32_t)(s * Cfg::A_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_BYTES);
@@ -405,7 +419,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
                 else ok = ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
                 const int off = ok ? ((b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch : 0;
                 tc::cp_async_16(a_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16),
-                                p.in + off, ok ? 16u : 0u);
+                                a_base + off, ok ? 16u : 0u);
                 if (!BORDER) { if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } } }
             }
 #pragma unroll
@@ -421,12 +435,13 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
                     row = ((size_t)bb * p.Ho + bho) * p.Wo + bwo;
                 }
                 tc::cp_async_16(b_st + (k >> 2) * ((BN / 32) * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
-                                p.dout + (ok ? row * N + nn : 0), ok ? 16u : 0u);
+                                b_base + (ok ? row * N + nn : 0), ok ? 16u : 0u);
             }
             tc::cp_async_arrive_noinc(bar_full + s);
             pix0 += 32;
             pwo += 32;
             while (pwo >= p.Wo) { pwo -= p.Wo; if (++pho == p.Ho) { pho = 0; ++pb; } }
+        }
         }
 
         // ------------------------------------------------------------------ epilogue: dw[o][mm] += D[mm][o]
@@ -451,7 +466,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         // ------------------------------------------------------------------ MMA issuer (warp 4)
         constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, BN, 1, 1);       // both operands MN-major
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
+            for (int kb = 0; kb < KB * npass; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 tc::mbar_wait(bar_full + s, ph);
@@ -494,194 +509,13 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t ra
     return fn(map, dtype, rank, gaddr, gdim, gstride, box, estr, il, sw, l2, oob);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// "wide" weight gradient (experimental, SCSFM_WGRAD_WIDE=1): the operand roles of the kernel above exchanged and the
-// (tap, channel) tile doubled.  A tcgen05.mma with both operands in shared memory costs ~140 cycles for M = 128 whatever
-// N is (measured on the forward kernel), so
-//     D[o (M = 128 lanes: output channels), (tap,c) (N = 256 columns)] += dout[pix, o]^T x gather(in)[pix, (tap,c)]
-// needs half the instructions of the M = (tap,c) / N = Cout arrangement for Cout = 128 and a quarter for Cout = 64.
-// Same MN-major BASE32B shared-memory layouts (atoms of 4 pixels x 32 channels, LBO = 512 B between atoms): the dout tile
-// always keeps four atoms per pixel group (M = 128; atoms beyond Cout hold stale shared memory and only feed unread
-// lanes), the gathered-input tile eight.  cp.async producers as above; the epilogue adds 16-byte vectors (red.v4.f32).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int WW_N = 256;                                 // (tap, c) columns per CTA
-struct WwCfg {
-    static constexpr int STAGES = 2;
-    static constexpr int A_BYTES = 32 * WW_N * 4;         // 32 pixels x 256 (tap,c): 8 pixel groups x 8 atoms x 512 B
-    static constexpr int B_BYTES = 32 * TBM * 4;          // 32 pixels x 128 output channels (4 atoms, BN/32 of them loaded)
-    static constexpr int TMEM_COLS = WW_N;
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
-};
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-template <int BN>      // output channels actually loaded per pixel row: 32, 64 or 128
-__global__ void __launch_bounds__(FW_THREADS)
-conv_wgrad_wide_tc_kernel(ScsfmConv p, int pix_per_split) {
-    using Cfg = WwCfg;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;                                    // gathered input, N side
-    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;            // dout, M side
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
-    uint64_t* bar_empty = bar_full + STAGES;
-    uint64_t* bar_acc = bar_empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Mtot = p.kh * p.kw * p.Cin, N = p.Cout, npix = p.B * p.Ho * p.Wo;
-    const int m0 = blockIdx.x * WW_N, n0 = blockIdx.y * TBM;
-    const int pix_begin = blockIdx.z * pix_per_split, pix_end = min(npix, pix_begin + pix_per_split);
-    const int KB = (pix_end - pix_begin + 31) / 32;
-    if (KB <= 0) return;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(bar_full + s, FW_PWARPS * 32);
-            tc::mbar_init(bar_empty + s, 1);
-        }
-        tc::mbar_init(bar_acc, 1);
-        tc::fence_barrier_init();
-    }
-    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    tc::fence_after_thread_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < FW_PWARPS) {
-        // ------------------------------------------------------------------ producers
-        // A: 64 chunk columns (4 consecutive (tap,c) entries each, fixed per thread) x 32 pixels; thread = chunk column
-        // tid % 64 and the 8 consecutive pixels 8 * (tid / 64) .. + 7 of the k-block.
-        constexpr int PPT = 8;
-        const int cidx = tid & 63, kq = tid >> 6;
-        const int mm = m0 + 4 * cidx;
-        const bool a_ok = mm < Mtot;
-        int a_dy = 0, a_dx = 0, a_ch = 0;
-        if (a_ok) {
-            const int tap = mm / p.Cin;
-            a_ch = mm - tap * p.Cin;
-            a_dy = tap / p.kw - p.pad;
-            a_dx = tap - (tap / p.kw) * p.kw - p.pad;
-        }
-        const bool reflect = p.pad_mode == PADMODE_REFLECT;
-        const uint32_t a_smem = tc::smem_u32(sA) + (uint32_t)((cidx >> 3) * 512);       // atom = cidx / 8
-        const int a_chunk = cidx & 7;
-        // B: BN/4 chunks per pixel row
-        constexpr int BCH = BN / 4;
-        constexpr int B_IT = (32 * BCH) / (FW_PWARPS * 32);
-        constexpr int B_STEP = (FW_PWARPS * 32) / BCH;
-        const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
-        const int nn = n0 + 4 * b_c4;
-        const bool b_ok = nn < N;
-        const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)((b_c4 >> 3) * 512);
-        int pb, pho, pwo;
-        {
-            const int px = pix_begin + PPT * kq;
-            pb = px / (p.Ho * p.Wo);
-            const int rem = px - pb * p.Ho * p.Wo;
-            pho = rem / p.Wo;
-            pwo = rem - pho * p.Wo;
-        }
-        int pix0 = pix_begin;
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            if (lane == 0) tc::mbar_wait(bar_empty + s, ph ^ 1);
-            __syncwarp();
-            const uint32_t a_st = a_smem + (uint32_t)(s * Cfg::A_BYTES), b_st = b_smem + (uint32_t)(s * Cfg::B_BYTES);
-            int b = pb, ho = pho, wo = pwo;
-#pragma unroll
-            for (int i = 0; i < PPT; ++i) {
-                const int k = PPT * kq + i;                 // pixel row inside the block: group k/4, row k%4
-                const int px = pix0 + k;
-                int hi = ho * p.stride + a_dy, wi = wo * p.stride + a_dx;
-                bool ok = a_ok && px < pix_end;
-                if (reflect) { hi = reflect_index(hi, p.Hi); wi = reflect_index(wi, p.Wi); }
-                else ok = ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
-                const int off = ok ? ((b * p.Hi + hi) * p.Wi + wi) * p.Cin + a_ch : 0;
-                tc::cp_async_16(a_st + (k >> 2) * (8 * 512) + (k & 3) * 128 + (((((a_chunk >> 1) ^ (k & 3)) << 1) | (a_chunk & 1)) * 16),
-                                p.in + off, ok ? 16u : 0u);
-                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } }
-            }
-#pragma unroll
-            for (int i = 0; i < B_IT; ++i) {
-                const int k = b_kr0 + B_STEP * i;
-                const int px = pix0 + k;
-                const bool ok = b_ok && px < pix_end;
-                tc::cp_async_16(b_st + (k >> 2) * (4 * 512) + (k & 3) * 128 + ((((((b_c4 & 7) >> 1) ^ (k & 3)) << 1) | (b_c4 & 1)) * 16),
-                                p.dout + (ok ? (size_t)px * N + nn : 0), ok ? 16u : 0u);
-            }
-            tc::cp_async_arrive_noinc(bar_full + s);
-            pix0 += 32;
-            pwo += 32;
-            while (pwo >= p.Wo) { pwo -= p.Wo; if (++pho == p.Ho) { pho = 0; ++pb; } }
-        }
-
-        // ------------------------------------------------------------------ epilogue: dw[o][mm .. mm+3] += D[o][mm .. mm+3]
-        tc::mbar_wait(bar_acc, 0);
-        tc::fence_after_thread_sync();
-        const int quarter = warp & 3, half = warp >> 2;
-        const int o = n0 + quarter * 32 + lane;
-        if (n0 + quarter * 32 < N) {                      // warp-uniform: this lane quarter holds real output channels
-#pragma unroll 1
-            for (int cc = half; cc < WW_N / 32; cc += FW_PWARPS / 4) {
-                if (m0 + cc * 32 >= Mtot) break;
-                uint32_t r[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
-                tc::tmem_ld_wait();
-                if (o < N) {
-                    float* dst = p.dw + (size_t)o * Mtot + m0 + cc * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (m0 + cc * 32 + j < Mtot)       // Mtot % 4 == 0: a vector never straddles the end
-                            red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, WW_N, 1, 1);       // both operands MN-major
-        if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                tc::mbar_wait(bar_full + s, ph);
-                tc::fence_proxy_async();
-                tc::fence_after_thread_sync();
-                const uint32_t a_addr = tc::smem_u32(sA + s * Cfg::A_BYTES);
-                const uint32_t b_addr = tc::smem_u32(sB + s * Cfg::B_BYTES);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {               // 4 x (2 pixel groups of 4): UMMA K = 8 for tf32
-                    // M side: dout, 4 atoms per pixel group (SBO = 4 * 512); N side: gathered input, 8 atoms (SBO = 8 * 512)
-                    const uint64_t dm = tc::make_smem_desc(b_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
-                    const uint64_t dn = tc::make_smem_desc(a_addr + j * (2 * 8 * 512), 512, 8 * 512, tc::LAYOUT_SW128_BASE32B);
-                    tc::mma_tf32(tmem_base, dm, dn, idesc, (kb | j) != 0 ? 1u : 0u);
-                }
-                tc::mma_commit(bar_empty + s);
-            }
-            tc::mma_commit(bar_acc);
-        }
-        __syncwarp();
-    }
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
-
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
 
 template <int BN, bool BORDER = false>
 static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     using Cfg = WgCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    SCSFM_CHECK_CUDA(attr_rc);
     const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * (BORDER ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     const int mt = (Mtot + TBM - 1) / TBM, nt = (p.Cout + BN - 1) / BN;
     int splits = (148 * 3 + mt * nt - 1) / (mt * nt);          // 3 CTAs per SM fit
@@ -695,36 +529,6 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     return SCSFM_OK;
 }
 
-template <int BN>
-static int launch_wgrad_wide_tc(const ScsfmConv& p, cudaStream_t st) {
-    using Cfg = WwCfg;
-    static bool configured = false;
-    if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_wide_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
-    const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * p.Ho * p.Wo;
-    const int mt = (Mtot + WW_N - 1) / WW_N, nt = (p.Cout + TBM - 1) / TBM;
-    int splits = (148 * 2 + mt * nt - 1) / (mt * nt);          // 2 CTAs per SM fit (96 KB of stages, 256 TMEM columns each)
-    const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
-    dim3 grid(mt, nt, (npix + pps - 1) / pps);
-    conv_wgrad_wide_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
-    SCSFM_CHECK_LAUNCH();
-    return SCSFM_OK;
-}
-
-static int g_wgrad_wide = -1;                   // -1: take SCSFM_WGRAD_WIDE from the environment on first use
-static int wgrad_wide_enabled() {               // experimental kernel, off unless SCSFM_WGRAD_WIDE=1 / scsfm_wgrad_config(1)
-    if (g_wgrad_wide < 0) {
-        const char* e = getenv("SCSFM_WGRAD_WIDE");
-        g_wgrad_wide = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
-    }
-    return g_wgrad_wide;
-}
-
 static TcView plain_view(const ScsfmConv& p) {
     return TcView{p.kh, p.kw, -p.pad, -p.pad, p.stride, 1, 0, 1, 0, p.Ho, p.Wo};
 }
@@ -732,21 +536,21 @@ static TcView plain_view(const ScsfmConv& p) {
 template <int BN>
 static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_fwd_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    SCSFM_CHECK_CUDA(attr_rc);
     const int M = p.B * (v.border ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     // TMA descriptor of the weight matrix [Cout rows][K columns] (K contiguous), box = 32 columns x BN rows, 128B swizzle
     const int K = v.kh * v.kw * p.Cin;
-    CUtensorMap wmap;
-    {
+    CUtensorMap wmap, wmap_lo;
+    for (int lo = 0; lo < 2; ++lo) {
+        const float* base = lo ? p.w_lo : p.w;
+        CUtensorMap& wmap_ = lo ? wmap_lo : wmap;
+        if (base == nullptr) { wmap_lo = wmap; continue; }
         const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)p.Cout};
         const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
         const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BN};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = encode_tiled(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.w), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&wmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -755,7 +559,7 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
         }
     }
     dim3 grid((M + TBM - 1) / TBM, (p.Cout + BN - 1) / BN);
-    conv_fwd_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, v, wmap);
+    conv_fwd_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, v, wmap, wmap_lo);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -779,7 +583,7 @@ static int tc_dispatch_gather(const ScsfmConv& p, const TcView& v, cudaStream_t 
 static int tc_dispatch(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     if (p.pad_mode == PADMODE_ZERO && conv_tma_eligible(p, v)) return launch_conv_tma(p, v, st);
     if (p.pad_mode == PADMODE_REFLECT && p.bn_sums == nullptr && p.Ho >= 3 && p.Wo >= 3 &&
-        (p.Ho * p.Wo >= 64 * 208 || conv_tma_forced()) && conv_tma_eligible(p, v)) {
+        (p.Ho * p.Wo >= 64 * 208 || conv_tma_forced(p)) && conv_tma_eligible(p, v)) {
         // reflection padding only changes the outermost ring of output pixels: run the TMA kernel with zero padding
         // (interior exact), then recompute the 2*(Ho+Wo)-4 border pixels per image with the reflecting gather kernel.
         // Measured (tools/check_conv_tma.py): pays off from 64x208 upwards; below that the ring is too large a share
@@ -814,12 +618,12 @@ extern "C" int scsfm_conv2d_fwd_tc(const ScsfmConv* p, void* stream) {
     return tc_dispatch(*p, plain_view(*p), (cudaStream_t)stream);
 }
 
-extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, void* stream) {
-    SCSFM_CHECK_ARG(w && wt && Cout > 0 && kh > 0 && kw > 0 && Cin > 0, "weight_flip: bad arguments");
+extern "C" int scsfm_weight_flip(const float* w, int Cout, int kh, int kw, int Cin, float* wt, int operand, void* stream) {
+    SCSFM_CHECK_ARG(w && wt && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && operand >= 0 && operand <= 2, "weight_flip: bad arguments");
     const long long total = (long long)Cout * kh * kw * Cin;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, kh, kw, kh - 1, kw - 1, 1, wt);
+    weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, kh, kw, kh - 1, kw - 1, 1, wt, operand);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -846,7 +650,7 @@ weight_flip_batched_kernel(const long long* __restrict__ table, int n) {
     const float* w = reinterpret_cast<const float*>(e[0]);
     float* wt = reinterpret_cast<float*>(e[1]);
     const int Co = (int)e[2], kh = (int)e[3], kw = (int)e[4], Ci = (int)e[5], jh = (int)e[6], jw = (int)e[7];
-    const int dy_max = (int)e[8], dx_max = (int)e[9], step = (int)e[10];
+    const int dy_max = (int)e[8], dx_max = (int)e[9], step = (int)(e[10] & 0xff), operand = (int)(e[10] >> 8);
     const int tco = (Co + 31) >> 5, tci = (Ci + 31) >> 5;
     int t = (int)((long long)blockIdx.x - e[11]);
     const int to = t % tco; t /= tco;
@@ -857,7 +661,7 @@ weight_flip_batched_kernel(const long long* __restrict__ table, int n) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int o = to * 32 + ty + 8 * k, c = tc * 32 + tx;
-        if (o < Co && c < Ci) tile[ty + 8 * k][tx] = tf32_round(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c));
+        if (o < Co && c < Ci) tile[ty + 8 * k][tx] = tc_operand(__ldg(w + (((size_t)o * kh + dy) * kw + dx) * Ci + c), operand);
     }
     __syncthreads();
 #pragma unroll
@@ -876,8 +680,8 @@ extern "C" int scsfm_weight_flip_batched(const long long* table, int n_rows, int
 
 // Stride-2 data gradient: wt4 receives the four parity-class weight sets back to back (class order (py,px) =
 // (0,0),(0,1),(1,0),(1,1)); total size = Cin*kh*kw*Cout floats, the same as the full flipped kernel.
-extern "C" int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, void* stream) {
-    SCSFM_CHECK_ARG(w && wt4 && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && pad >= 0, "weight_flip_s2: bad arguments");
+extern "C" int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, int Cin, int pad, float* wt4, int operand, void* stream) {
+    SCSFM_CHECK_ARG(w && wt4 && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && pad >= 0 && operand >= 0 && operand <= 2, "weight_flip_s2: bad arguments");
     size_t off = 0;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
@@ -889,7 +693,7 @@ extern "C" int scsfm_weight_flip_s2(const float* w, int Cout, int kh, int kw, in
             if (total > 0) {
                 int grid = (int)((total + 255) / 256);
                 if (grid > 148 * 16) grid = 148 * 16;
-                weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, 2, wt4 + off);
+                weight_flip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, 2, wt4 + off, operand);
                 SCSFM_CHECK_LAUNCH();
             }
             off += (size_t)total;
@@ -905,7 +709,8 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG(p->kh == p->kw && p->kh - 1 - p->pad >= 0, "conv2d_dgrad_tc: square kernels only");
     cudaStream_t st = (cudaStream_t)stream;
     ScsfmConv q = *p;
-    q.in = p->dout; q.out = p->din; q.bias = nullptr; q.bn_sums = nullptr; q.act = SCSFM_ACT_NONE;
+    q.in = p->dout; q.in_lo = p->dout_lo; q.out = p->din; q.bias = nullptr; q.bn_sums = nullptr; q.act = SCSFM_ACT_NONE;
+    q.dout_lo = nullptr;                       // (w_lo: the flipped low-part weights, laid out like w)
     q.Hi = p->Ho; q.Wi = p->Wo; q.Cin = p->Cout;
     q.Cout = p->Cin; q.pad_mode = SCSFM_PADMODE_ZERO;
     if (p->stride == 1) {
@@ -947,6 +752,7 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
             if (jh > 0 && jw > 0 && Hs > 0 && Ws > 0) {
                 ScsfmConv r = q;
                 r.w = p->w + woff;
+                r.w_lo = p->w_lo ? p->w_lo + woff : nullptr;
                 r.Ho = Hs; r.Wo = Ws; r.kh = jh; r.kw = jw;
                 // input (dout) row of output hy and tap jy: hy + (py + pad - dy_max)/2 + jy
                 TcView v{jh, jw, (py + p->pad - dy_max) / 2, (px + p->pad - dx_max) / 2, 1, 2, py, 2, px, p->Hi, p->Wi};
@@ -954,14 +760,6 @@ extern "C" int scsfm_conv2d_dgrad_tc(const ScsfmConv* p, void* stream) {
             }
             woff += wcount;
         }
-    return SCSFM_OK;
-}
-
-// experiment hook: 0 the default kernel, 1 the wide one (output channels on M, 256 (tap,c) columns on N, cp.async
-// producers), 2 the TMA one (conv_wgrad_tma.cu; layers it does not take fall back to the default)
-extern "C" int scsfm_wgrad_config(int wide) {
-    SCSFM_CHECK_ARG(wide >= 0 && wide <= 2, "wgrad_config: bad arguments");
-    g_wgrad_wide = wide;
     return SCSFM_OK;
 }
 
@@ -977,9 +775,10 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     int rc;
     ScsfmConv zp = *p;                         // the same layer with zero padding (what the TMA kernel computes)
     zp.pad_mode = SCSFM_PADMODE_ZERO;
-    if (wgrad_wide_enabled() == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
+    const int kernel = (int)((p->tune >> 12) & 3u);       // SCSFM_TUNE_WGRAD: 0 auto, 1 cp.async kernel, 2 TMA kernel
+    if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
-    } else if (wgrad_wide_enabled() == 2 && p->pad_mode == PADMODE_REFLECT && p->pad == 1 && p->Ho >= 3 && p->Wo >= 3 &&
+    } else if (kernel == 2 && p->pad_mode == PADMODE_REFLECT && p->pad == 1 && p->Ho >= 3 && p->Wo >= 3 &&
                p->Ho * p->Wo >= 64 * 208 && conv_wgrad_tma_eligible(zp)) {
         // reflection padding: zero-padded pass + the contributions of the taps that leave the image (border pixels only)
         rc = launch_conv_wgrad_tma(zp, st);
@@ -988,10 +787,6 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
             else if (p->Cout <= 64) rc = launch_wgrad_tc<64, true>(*p, st);
             else rc = launch_wgrad_tc<128, true>(*p, st);
         }
-    } else if (wgrad_wide_enabled() == 1) {
-        if (p->Cout <= 32) rc = launch_wgrad_wide_tc<32>(*p, st);
-        else if (p->Cout <= 64) rc = launch_wgrad_wide_tc<64>(*p, st);
-        else rc = launch_wgrad_wide_tc<128>(*p, st);
     } else if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
     else if (p->Cout <= 64) rc = launch_wgrad_tc<64>(*p, st);
     else rc = launch_wgrad_tc<128>(*p, st);

@@ -66,7 +66,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t ra
 
 // conv_tma.cu: stride-1 zero-padded (sub-)convolutions with kh, kw <= 3 through the TMA halo-patch kernel
 bool conv_tma_eligible(const ScsfmConv& p, const TcView& v);
-bool conv_tma_forced();      // a tile configuration is being forced through scsfm_conv_tma_config (tests / experiments)
+bool conv_tma_forced(const ScsfmConv& p);      // a tile configuration is being forced through ScsfmConv.tune (tests / experiments)
 int launch_conv_tma(const ScsfmConv& p, const TcView& v, cudaStream_t st);
 
 // conv_wgrad_tma.cu (experimental): stride-1 zero-padded weight gradient with TMA-delivered operands

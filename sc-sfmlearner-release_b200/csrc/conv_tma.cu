@@ -49,7 +49,10 @@ struct TmaGeom {
     int n_tiles, num_work;   // Cout tiles; work items = B * tiles_y * tiles_x * n_tiles (Cout tile fastest)
     int stages;              // shared-memory ring depth
     int a_bytes, stage_bytes;
-    unsigned long long* dbg; // optional per-CTA cycle counters (scsfm_conv_tma_debug), 8 per CTA; NULL = off
+    // split-accumulate passes per (channel chunk, dx): pass i multiplies (activations: lo if a_lo bit i else raw) by
+    // (weights: lo if w_lo bit i else raw); plain TF32 = one pass with both masks 0
+    int npass, a_lo, w_lo;
+    unsigned long long* dbg; // optional per-CTA cycle counters (ScsfmConv.debug), 8 per CTA; NULL = off
 };
 
 __device__ __forceinline__ long long tma_clock() { return clock64(); }
@@ -59,7 +62,8 @@ __device__ __forceinline__ long long tma_clock() { return clock64(); }
 // MT: 128-pixel sub-tiles stacked vertically, N = MT * 128 pixels per instruction.
 template <int BNW, int MT>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap) {
+conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                const __grid_constant__ CUtensorMap amap_lo, const __grid_constant__ CUtensorMap wmap_lo) {
     constexpr int NPIX = MT * TBM;                           // TMEM columns of one accumulator buffer
     constexpr int TMEM_COLS = 2 * NPIX;                      // 256 or 512
     constexpr int W_TILE = BNW * 128;                         // one tap: BNW rows x 32 floats
@@ -104,6 +108,8 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
         if (lane == 0) {
             tc::tma_prefetch_desc(&amap);
             tc::tma_prefetch_desc(&wmap);
+            if (g.a_lo) tc::tma_prefetch_desc(&amap_lo);
+            if (g.w_lo) tc::tma_prefetch_desc(&wmap_lo);
             const uint32_t tx_bytes = (uint32_t)(patch_rows * TW * 128 + v.kh * W_TILE);
             int s = 0;
             uint32_t ph = 0;
@@ -118,16 +124,20 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                 const int y0 = ty * (MT * TH) + v.oy0, x0 = tx * TW + v.ox0;
                 for (int ck = 0; ck < chunks; ++ck) {
                     for (int dx = 0; dx < v.kw; ++dx) {
-                        const long long t0 = g.dbg ? tma_clock() : 0;
-                        tc::mbar_wait(bar_empty + s, ph ^ 1);
-                        if (g.dbg) t_wait += tma_clock() - t0;
-                        const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
-                        tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
-                        tc::tma_load_4d(st, &amap, ck * TBK, x0 + dx, y0, b, bar_full + s);
-                        for (int dy = 0; dy < v.kh; ++dy)
-                            tc::tma_load_2d(st + (uint32_t)(g.a_bytes + dy * W_TILE), &wmap, (dy * v.kw + dx) * p.Cin + ck * TBK, n0,
-                                            bar_full + s);
-                        if (++s == g.stages) { s = 0; ph ^= 1; }
+                        for (int ps = 0; ps < g.npass; ++ps) {
+                            const CUtensorMap* am = ((g.a_lo >> ps) & 1) ? &amap_lo : &amap;
+                            const CUtensorMap* wm = ((g.w_lo >> ps) & 1) ? &wmap_lo : &wmap;
+                            const long long t0 = g.dbg ? tma_clock() : 0;
+                            tc::mbar_wait(bar_empty + s, ph ^ 1);
+                            if (g.dbg) t_wait += tma_clock() - t0;
+                            const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
+                            tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
+                            tc::tma_load_4d(st, am, ck * TBK, x0 + dx, y0, b, bar_full + s);
+                            for (int dy = 0; dy < v.kh; ++dy)
+                                tc::tma_load_2d(st + (uint32_t)(g.a_bytes + dy * W_TILE), wm, (dy * v.kw + dx) * p.Cin + ck * TBK, n0,
+                                                bar_full + s);
+                            if (++s == g.stages) { s = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -160,23 +170,25 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                     const int rem = p.Cin - ck * TBK;
                     const int k8 = rem >= TBK ? TBK / 8 : (rem + 7) / 8;           // K8 slices holding real channels
                     for (int dx = 0; dx < v.kw; ++dx) {
-                        const long long t0 = g.dbg ? tma_clock() : 0;
-                        tc::mbar_wait(bar_full + s, ph);
-                        if (g.dbg) t_full += tma_clock() - t0;
-                        tc::fence_after_thread_sync();
-                        const uint32_t x_addr = ring_base + (uint32_t)(s * g.stage_bytes);
-                        const uint32_t w_addr = x_addr + (uint32_t)g.a_bytes;
-                        for (int dy = 0; dy < v.kh; ++dy) {
-                            uint64_t dw = desc0 + (uint64_t)((w_addr + (uint32_t)(dy * W_TILE)) >> 4);      // M side: weights
-                            uint64_t dx_ = desc0 + (uint64_t)((x_addr + (uint32_t)dy * dy_bytes) >> 4);    // N side: pixels
-                            for (int q = 0; q < k8; ++q) {
-                                tc::mma_tf32(acc, dw, dx_, idesc, (ck | dx | dy | q) != 0 ? 1u : 0u);
-                                dw += 2;                     // next K8 slice: +32 bytes inside the 128-byte swizzle row
-                                dx_ += 2;
+                        for (int ps = 0; ps < g.npass; ++ps) {
+                            const long long t0 = g.dbg ? tma_clock() : 0;
+                            tc::mbar_wait(bar_full + s, ph);
+                            if (g.dbg) t_full += tma_clock() - t0;
+                            tc::fence_after_thread_sync();
+                            const uint32_t x_addr = ring_base + (uint32_t)(s * g.stage_bytes);
+                            const uint32_t w_addr = x_addr + (uint32_t)g.a_bytes;
+                            for (int dy = 0; dy < v.kh; ++dy) {
+                                uint64_t dw = desc0 + (uint64_t)((w_addr + (uint32_t)(dy * W_TILE)) >> 4);      // M side: weights
+                                uint64_t dx_ = desc0 + (uint64_t)((x_addr + (uint32_t)dy * dy_bytes) >> 4);    // N side: pixels
+                                for (int q = 0; q < k8; ++q) {
+                                    tc::mma_tf32(acc, dw, dx_, idesc, (ck | dx | ps | dy | q) != 0 ? 1u : 0u);
+                                    dw += 2;                     // next K8 slice: +32 bytes inside the 128-byte swizzle row
+                                    dx_ += 2;
+                                }
                             }
+                            tc::mma_commit(bar_empty + s);
+                            if (++s == g.stages) { s = 0; ph ^= 1; }
                         }
-                        tc::mma_commit(bar_empty + s);
-                        if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
                 }
                 tc::mma_commit(acc_full + buf);
@@ -311,22 +323,20 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static int env_enable() {                     // SCSFM_CONV_TMA=0 routes every layer through the gather kernel
-    const char* e = getenv("SCSFM_CONV_TMA");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
-}
-static int g_tma_enable = env_enable(), g_force_mt = 0, g_force_bn = 0, g_force_tw = 0;
-static unsigned long long* g_dbg = nullptr;
+// per-call knobs (ScsfmConv.tune, include/scsfm.h): no process-global state
+static int tune_mt(const ScsfmConv& p) { return (int)((p.tune >> 4) & 3u); }
+static int tune_tw(const ScsfmConv& p) { const int t = (int)((p.tune >> 6) & 3u); return t ? t + 2 : 0; }
+static int tune_bn(const ScsfmConv& p) { const int t = (int)((p.tune >> 8) & 15u); return t ? 8 << t : 0; }
 
 bool conv_tma_eligible(const ScsfmConv& p, const TcView& v) {
-    if (!g_tma_enable || v.border) return false;
+    if ((p.tune & SCSFM_TUNE_NO_TMA) || v.border) return false;
     if (v.in_stride != 1 || v.kh > TMA_MAX_KH || v.kw > TMA_MAX_KH || v.kh < 1 || v.kw < 1) return false;
     if ((p.Cin & 3) != 0 || (p.Cout & 3) != 0) return false;      // 16-byte TMA rows / float4 epilogue
     if (p.bn_sums && p.B % (p.bn_groups > 0 ? p.bn_groups : 1) != 0) return false;
     return true;
 }
 
-bool conv_tma_forced() { return g_force_mt != 0 || g_force_bn != 0 || g_force_tw != 0; }
+bool conv_tma_forced(const ScsfmConv& p) { return tune_mt(p) != 0 || tune_bn(p) != 0 || tune_tw(p) != 0; }
 
 static int sm_count() {
     static int n = 0;
@@ -339,11 +349,9 @@ static int sm_count() {
 
 template <int BNW, int MT>
 static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_tma_kernel<BNW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_MAX));
-        configured = true;
-    }
+    // one-time opt-in to 227 KB of dynamic shared memory (C++11 thread-safe static initialisation)
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_tma_kernel<BNW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_MAX);
+    SCSFM_CHECK_CUDA(attr_rc);
     const int TW = 1 << tw_log2, TH = TBM >> tw_log2;
     TmaGeom g;
     g.tw_log2 = tw_log2;
@@ -362,16 +370,23 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
         set_error("conv_tma: stage of %d bytes does not fit twice in shared memory", g.stage_bytes);
         return SCSFM_ERR_ARG;
     }
-    g.dbg = g_dbg;
+    g.dbg = p.debug;
+    // split-accumulate passes: raw x raw, then lo(activations) x raw(weights), then raw(activations) x lo(weights)
+    g.npass = 1; g.a_lo = 0; g.w_lo = 0;
+    if (p.in_lo != nullptr) { g.a_lo |= 1 << g.npass; ++g.npass; }
+    if (p.w_lo != nullptr) { g.w_lo |= 1 << g.npass; ++g.npass; }
     const size_t smem = (size_t)fixed + (size_t)g.stages * g.stage_bytes;
-    CUtensorMap amap, wmap;
-    {
+    CUtensorMap amap, wmap, amap_lo, wmap_lo;
+    for (int lo = 0; lo < 2; ++lo) {
+        const float* base = lo ? p.in_lo : p.in;
+        CUtensorMap& amap_ = lo ? amap_lo : amap;
+        if (base == nullptr) { amap_lo = amap; continue; }
         // activations [B][Hi][Wi][Cin] (Cin contiguous); box = 32 channels x TW x (MT*TH + kh - 1) x 1, 128B swizzle
         const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.B};
         const cuuint64_t gstride[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Wi * p.Cin * 4, (cuuint64_t)p.Hi * p.Wi * p.Cin * 4};
         const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)TW, (cuuint32_t)(MT * TH + v.kh - 1), 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = encode_tiled(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&amap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -379,14 +394,17 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
             return SCSFM_ERR_CUDA;
         }
     }
-    {
+    for (int lo = 0; lo < 2; ++lo) {
+        const float* base = lo ? p.w_lo : p.w;
+        CUtensorMap& wmap_ = lo ? wmap_lo : wmap;
+        if (base == nullptr) { wmap_lo = wmap; continue; }
         // weights [Cout][K] (K contiguous); box = 32 columns x BNW rows (rows past Cout are zero-filled)
         const int K = v.kh * v.kw * p.Cin;
         const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)p.Cout};
         const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
         const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BNW};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = encode_tiled(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.w), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&wmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -396,7 +414,7 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
     }
     int ctas = sm_count();
     if (ctas > g.num_work) ctas = g.num_work;
-    conv_tma_kernel<BNW, MT><<<ctas, TMA_THREADS, smem, st>>>(p, v, g, amap, wmap);
+    conv_tma_kernel<BNW, MT><<<ctas, TMA_THREADS, smem, st>>>(p, v, g, amap, wmap, amap_lo, wmap_lo);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -426,9 +444,9 @@ int launch_conv_tma(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
             const double cost = (double)waves + 0.05 * area + 0.01 * mt;
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_mt = mt; best_tw = twl; }
         }
-    if (g_force_mt) best_mt = g_force_mt;
-    if (g_force_tw) best_tw = g_force_tw;
-    if (g_force_bn) bnw = g_force_bn < bnw ? bnw : g_force_bn;       // never fewer rows than the Cout tile needs
+    if (tune_mt(p)) best_mt = tune_mt(p);
+    if (tune_tw(p)) best_tw = tune_tw(p);
+    if (tune_bn(p)) bnw = tune_bn(p) < bnw ? bnw : tune_bn(p);       // never fewer rows than the Cout tile needs
     if (best_mt == 1) {
         switch (bnw) {
             case 16: return launch_tma_cfg<16, 1>(p, v, best_tw, st);
@@ -447,25 +465,3 @@ int launch_conv_tma(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
 
 }  // namespace scsfm
 
-// Experiment / test hook: enable = 0 routes everything through the cp.async kernel; force_* = 0 keeps the heuristic
-// (force_mt in {1,2}: pixels per MMA = 128 / 256; force_bn in {16,32,64,128}: weight rows kept in shared memory, raised
-// to what Cout needs; force_tw_log2 in {3,4}).
-extern "C" int scsfm_conv_tma_config(int enable, int force_mt, int force_bn, int force_tw_log2) {
-    SCSFM_CHECK_ARG((force_mt >= 0 && force_mt <= 2) && (force_bn == 0 || force_bn == 16 || force_bn == 32 || force_bn == 64 || force_bn == 128) &&
-                        (force_tw_log2 == 0 || force_tw_log2 == 3 || force_tw_log2 == 4),
-                    "conv_tma_config: bad arguments");
-    scsfm::g_tma_enable = enable;
-    scsfm::g_force_mt = force_mt;
-    scsfm::g_force_bn = force_bn;
-    scsfm::g_force_tw = force_tw_log2;
-    return SCSFM_OK;
-}
-
-// Profiling hook: buf = device array of 8 x (number of SMs) 64-bit counters, or NULL to switch it off.  Per CTA (clock64
-// cycles): [0] producer waiting for a free stage, [1] producer total, [2] MMA thread waiting for operands, [3] MMA thread
-// waiting for a drained accumulator, [4] MMA thread total, [5] epilogue warp 0 waiting for an accumulator, [6] epilogue
-// total, [7] tiles processed.
-extern "C" int scsfm_conv_tma_debug(unsigned long long* buf) {
-    scsfm::g_dbg = buf;
-    return SCSFM_OK;
-}

@@ -1,5 +1,5 @@
-// EXPERIMENTAL (scsfm_wgrad_config(2) / SCSFM_WGRAD_WIDE=2; not validated on a GPU yet, never selected by default):
-// weight gradient of a stride-1, zero-padded convolution with both operands delivered by TMA.
+// Weight gradient of a stride-1, zero-padded convolution with both operands delivered by TMA (selected per call with
+// SCSFM_TUNE_WGRAD(2); validated on B200 against the cp.async kernel and fp64, profiles/r02_wgrad_tma_check.txt).
 //
 //   D[o (M = 128 TMEM lanes: output channels), (dy, chunk c, ch) (N = kh * G * 32 columns)] +=
 //        sum over the pixels p of a tile   dout[p, o] * in[p + (dy, dx) - pad, 32 * (G * cg + c) + ch]
@@ -35,10 +35,12 @@ struct WtGeom {
     int groups, G;               // channel-chunk groups of G chunks (the last group may hold fewer real chunks)
     int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4)
     int stages, patch_bytes, stage_bytes;
+    int npass, x_lo, d_lo;       // split-accumulate passes per tile: pass i uses lo(input) if x_lo bit i, lo(dout) if d_lo bit i
 };
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
-conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dmap) {
+conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dmap,
+                      const __grid_constant__ CUtensorMap xmap_lo, const __grid_constant__ CUtensorMap dmap_lo) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);
@@ -89,19 +91,23 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                 const int ty = q % g.tiles_y;
                 const int b = q / g.tiles_y;
                 const int y0 = ty * TH, x0 = tx * TW;
-                tc::mbar_wait(bar_empty + s, ph ^ 1);
-                const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
-                tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
-                // M side: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
-                for (int a = 0; a < g.atoms_m; ++a)
-                    tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
-                // N side: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
-                const uint32_t pst = st + WT_DOUT_BYTES;
-                for (int r = 0; r < prows; ++r)
-                    for (int c = 0; c < g.G; ++c)
-                        tc::tma_load_4d(pst + (uint32_t)(r * g.G + c) * row_bytes, &xmap, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
-                                        bar_full + s);
-                if (++s == g.stages) { s = 0; ph ^= 1; }
+                for (int ps = 0; ps < g.npass; ++ps) {
+                    const CUtensorMap* xm = ((g.x_lo >> ps) & 1) ? &xmap_lo : &xmap;
+                    const CUtensorMap* dm = ((g.d_lo >> ps) & 1) ? &dmap_lo : &dmap;
+                    tc::mbar_wait(bar_empty + s, ph ^ 1);
+                    const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
+                    tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
+                    // M side: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
+                    for (int a = 0; a < g.atoms_m; ++a)
+                        tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                    // N side: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
+                    const uint32_t pst = st + WT_DOUT_BYTES;
+                    for (int r = 0; r < prows; ++r)
+                        for (int c = 0; c < g.G; ++c)
+                            tc::tma_load_4d(pst + (uint32_t)(r * g.G + c) * row_bytes, xm, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
+                                            bar_full + s);
+                    if (++s == g.stages) { s = 0; ph ^= 1; }
+                }
             }
         }
         __syncwarp();
@@ -115,7 +121,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             const int slices = TW >> 3;                       // 8-pixel slices per tile row
             int s = 0;
             uint32_t ph = 0;
-            for (int t = t_begin; t < t_end; ++t) {
+            for (int it = 0; it < ntiles * g.npass; ++it) {
                 tc::mbar_wait(bar_full + s, ph);
                 tc::fence_after_thread_sync();
                 const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
@@ -124,7 +130,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                     for (int kq = 0; kq < slices; ++kq) {
                         const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
                         const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
-                        tc::mma_tf32(tmem_base, dm, dn, idesc, (t != t_begin || r != 0 || kq != 0) ? 1u : 0u);
+                        tc::mma_tf32(tmem_base, dm, dn, idesc, (it != 0 || r != 0 || kq != 0) ? 1u : 0u);
                     }
                 }
                 tc::mma_commit(bar_empty + s);
@@ -172,11 +178,8 @@ bool conv_wgrad_tma_eligible(const ScsfmConv& p) {
 }
 
 int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SCSFM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX));
-        configured = true;
-    }
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX);
+    SCSFM_CHECK_CUDA(attr_rc);
     WtGeom g;
     // tile shape: least padded area
     const long a16 = (long)((p.Ho + 7) / 8 * 8) * ((p.Wo + 15) / 16 * 16), a8 = (long)((p.Ho + 15) / 16 * 16) * ((p.Wo + 7) / 8 * 8);
@@ -207,13 +210,19 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     if (splits < 1) splits = 1;
     g.tiles_per_split = (g.tiles_total + splits - 1) / splits;
     splits = (g.tiles_total + g.tiles_per_split - 1) / g.tiles_per_split;
-    CUtensorMap xmap, dmap;
-    {
+    g.npass = 1; g.x_lo = 0; g.d_lo = 0;
+    if (p.in_lo != nullptr) { g.x_lo |= 1 << g.npass; ++g.npass; }
+    if (p.dout_lo != nullptr) { g.d_lo |= 1 << g.npass; ++g.npass; }
+    CUtensorMap xmap, dmap, xmap_lo, dmap_lo;
+    for (int lo = 0; lo < 2; ++lo) {
+        const float* base = lo ? p.in_lo : p.in;
+        CUtensorMap& xmap_ = lo ? xmap_lo : xmap;
+        if (base == nullptr) { xmap_lo = xmap; continue; }
         const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.B};
         const cuuint64_t gstride[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Wi * p.Cin * 4, (cuuint64_t)p.Hi * p.Wi * p.Cin * 4};
         const cuuint32_t box[4] = {32, (cuuint32_t)TW, 1, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = encode_tiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&xmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -221,12 +230,15 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
             return SCSFM_ERR_CUDA;
         }
     }
-    {
+    for (int lo = 0; lo < 2; ++lo) {
+        const float* base = lo ? p.dout_lo : p.dout;
+        CUtensorMap& dmap_ = lo ? dmap_lo : dmap;
+        if (base == nullptr) { dmap_lo = dmap; continue; }
         const cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
         const cuuint64_t gstride[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.Wo * p.Cout * 4, (cuuint64_t)p.Ho * p.Wo * p.Cout * 4};
         const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = encode_tiled(&dmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.dout), gdim, gstride, box, estr,
+        const CUresult r = encode_tiled(&dmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -236,7 +248,7 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     }
     const size_t smem = 2048 + (size_t)g.stages * g.stage_bytes;
     dim3 grid(g.groups * p.kw, nt, splits);
-    conv_wgrad_tma_kernel<<<grid, WT_THREADS, smem, st>>>(p, g, xmap, dmap);
+    conv_wgrad_tma_kernel<<<grid, WT_THREADS, smem, st>>>(p, g, xmap, dmap, xmap_lo, dmap_lo);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

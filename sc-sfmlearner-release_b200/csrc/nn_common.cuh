@@ -17,4 +17,11 @@ __device__ __forceinline__ float tf32_round(float x) {
     return __uint_as_float(u);
 }
 __device__ __forceinline__ float maybe_round(float x, bool on) { return on ? tf32_round(x) : x; }
+// what kind::tf32 reads of an fp32 operand: the upper 19 bits (sign, exponent, 10 mantissa bits)
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// low part of the split-accumulate operands: x = trunc(x) + (x - trunc(x)) exactly; the remainder has <= 13 significant
+// bits and is itself rounded to TF32 (residual <= 2^-21 |x|)
+__device__ __forceinline__ float tf32_lo(float x) { return tf32_round(x - tf32_trunc(x)); }
+// SCSFM_OPERAND_*: 0 = rounded TF32, 1 = raw bits, 2 = low part
+__device__ __forceinline__ float tc_operand(float x, int kind) { return kind == 0 ? tf32_round(x) : (kind == 1 ? x : tf32_lo(x)); }
 }  // namespace scsfm

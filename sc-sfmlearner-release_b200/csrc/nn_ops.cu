@@ -35,7 +35,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __
 // [B,C,H,W] (x1 or x2 sources) -> NHWC with the channel count padded to Cpad (zeros): the 7x7 stems run on the tensor
 // cores with Cin 3 -> 4 / 6 -> 8
 __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int C, int HW, int Cpad,
-                                        float* __restrict__ out) {
+                                        float* __restrict__ out, int operand) {
     const int Ct = C * (b ? 2 : 1);
     const long long total = (long long)B * HW * Cpad;
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -46,19 +46,19 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ a, const float
         if (c < Ct) {
             const float* src = c < C ? a : b;
             const int cc = c < C ? c : c - C;
-            v = tf32_round(__ldg(src + ((size_t)bb * C + cc) * HW + p));
+            v = tc_operand(__ldg(src + ((size_t)bb * C + cc) * HW + p), operand);
         }
         out[i] = v;
     }
 }
 
 // rows of C floats -> rows of Cpad floats (zero padded, TF32 rounded): stem weights [64*49][3] -> [64*49][4]
-__global__ void pad_channels_kernel(const float* __restrict__ src, long long rows, int C, int Cpad, float* __restrict__ dst) {
+__global__ void pad_channels_kernel(const float* __restrict__ src, long long rows, int C, int Cpad, float* __restrict__ dst, int operand) {
     const long long total = rows * Cpad;
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
         const int c = (int)(i % Cpad);
         const long long r = i / Cpad;
-        dst[i] = c < C ? tf32_round(__ldg(src + r * C + c)) : 0.f;
+        dst[i] = c < C ? tc_operand(__ldg(src + r * C + c), operand) : 0.f;
     }
 }
 
@@ -557,10 +557,19 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
     for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) out[i] = tf32_round(__ldg(in + i));
 }
 
+// ----- low part of a split-accumulate operand: lo = tf32(x - trunc_tf32(x)), 16 bytes per thread and iteration ---------
+__global__ void __launch_bounds__(NT) split_tf32_kernel(const float* __restrict__ in, float* __restrict__ lo, long long n4, long long n) {
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(in) + i);
+        reinterpret_cast<float4*>(lo)[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - 4 * n4)) lo[4 * n4 + threadIdx.x] = tf32_lo(__ldg(in + 4 * n4 + threadIdx.x));
+}
+
 // ----- Adam ---------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, int step_host,
-                            const int* __restrict__ step_dev, float* __restrict__ p_tf32) {
+                            const int* __restrict__ step_dev, float* __restrict__ mirror, int mirror_operand) {
     // torch.optim.Adam (non-amsgrad): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
     // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  The step count may live on the device so that a captured
     // CUDA graph of the training step stays valid across replays.
@@ -578,7 +587,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         v[i] = vv;
         const float pn = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
         p[i] = pn;
-        if (p_tf32 != nullptr) p_tf32[i] = tf32_round(pn);      // operand mirror of the tensor-core convolutions
+        if (mirror != nullptr) mirror[i] = tc_operand(pn, mirror_operand);      // operand mirror of the tensor-core convolutions
     }
 }
 
@@ -595,16 +604,16 @@ extern "C" int scsfm_nchw_to_nhwc(const float* a, const float* b, int B, int C, 
     return SCSFM_OK;
 }
 
-extern "C" int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, void* stream) {
-    SCSFM_CHECK_ARG(a && out && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C * (b ? 2 : 1), "nchw_to_nhwc_pad: bad arguments");
-    nchw_to_nhwc_pad_kernel<<<grid_for((long long)B * H * W * Cpad), NT, 0, ST>>>(a, b, B, C, H * W, Cpad, out);
+extern "C" int scsfm_nchw_to_nhwc_pad(const float* a, const float* b, int B, int C, int H, int W, int Cpad, float* out, int operand, void* stream) {
+    SCSFM_CHECK_ARG(a && out && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C * (b ? 2 : 1) && operand >= 0 && operand <= 2, "nchw_to_nhwc_pad: bad arguments");
+    nchw_to_nhwc_pad_kernel<<<grid_for((long long)B * H * W * Cpad), NT, 0, ST>>>(a, b, B, C, H * W, Cpad, out, operand);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
 
-extern "C" int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, void* stream) {
-    SCSFM_CHECK_ARG(src && dst && rows > 0 && C > 0 && Cpad >= C, "pad_channels: bad arguments");
-    pad_channels_kernel<<<grid_for(rows * Cpad), NT, 0, ST>>>(src, rows, C, Cpad, dst);
+extern "C" int scsfm_pad_channels(const float* src, long long rows, int C, int Cpad, float* dst, int operand, void* stream) {
+    SCSFM_CHECK_ARG(src && dst && rows > 0 && C > 0 && Cpad >= C && operand >= 0 && operand <= 2, "pad_channels: bad arguments");
+    pad_channels_kernel<<<grid_for(rows * Cpad), NT, 0, ST>>>(src, rows, C, Cpad, dst, operand);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -769,11 +778,22 @@ extern "C" int scsfm_round_tf32(const float* in, float* out, long long n, void* 
     return SCSFM_OK;
 }
 
+extern "C" int scsfm_split_tf32(const float* in, float* lo, long long n, void* stream) {
+    SCSFM_CHECK_ARG(in && lo && n > 0, "split_tf32: bad arguments");
+    SCSFM_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0, "split_tf32: buffers must be 16-byte aligned");
+    const long long n4 = n / 4;
+    split_tf32_kernel<<<grid_for(n4 > 0 ? n4 : 1), NT, 0, ST>>>(in, lo, n4, n);
+    SCSFM_CHECK_LAUNCH();
+    return SCSFM_OK;
+}
+
 extern "C" int scsfm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                               float* param_tf32, void* stream) {
+                               float* mirror, int mirror_operand, void* stream) {
     SCSFM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
-    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev, param_tf32);
+    SCSFM_CHECK_ARG(mirror_operand == SCSFM_OPERAND_TF32 || mirror_operand == SCSFM_OPERAND_LO, "adam_step: bad mirror operand kind");
+    adam_kernel<<<grid_for(n), NT, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev, mirror,
+                                            mirror_operand);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

@@ -43,6 +43,9 @@ class GradExchange:
             grad_arena.div_(self.world)
             self._works.append(dist.all_reduce(grad_arena, op=dist.ReduceOp.SUM, async_op=True))
 
+    def pending(self):
+        return len(self._works)
+
     def wait(self):
         for w in self._works:
             w.wait()

@@ -48,10 +48,15 @@ class ConvParams(nn.Module):
         """[Cout,kh,kw,Cin] contiguous view of the channels-last weight (no copy)."""
         return self.weight.permute(0, 2, 3, 1)
 
-    def w_op(self):
-        """Weights as the conv kernels' B operand: in tf32 mode the per-call TF32-rounded copy of the arena."""
+    def w_op(self, cx):
+        """Weights as the conv kernels' operand: in tf32 mode the TF32-rounded mirror of the arena, otherwise the raw
+        parameters (fp32: exact kernels; tf32x3: the tensor core reads their high part)."""
         tc = getattr(self, "_tc_view", None)
-        return tc if (tc is not None and O.CONFIG["conv_mode"] == "tf32") else self.w_khwc()
+        return tc if (tc is not None and cx.mode == "tf32") else self.w_khwc()
+
+    def w_lo(self, cx):
+        """tf32x3 mode: the low part of the weights (the mirror arena holds it in that mode); None otherwise."""
+        return self._tc_view if cx.split else None
 
 
 class BNParams(nn.Module):
@@ -117,11 +122,29 @@ class ResnetEncoder(nn.Module):
         super().__init__()
         if num_layers not in STAGE_BLOCKS:
             raise ValueError("{} is not a valid number of resnet layers".format(num_layers))
-        if pretrained:
-            raise RuntimeError("ImageNet weights cannot be downloaded here (no network); construct with "
-                               "pretrained=False / --with-pretrain 0 and load a checkpoint instead")
         self.num_ch_enc = [64, 64, 128, 256, 512] if num_layers <= 34 else [64, 256, 512, 1024, 2048]
         self.encoder = Trunk(num_layers, 3 * num_input_images)
+        if pretrained:
+            self.load_imagenet(num_layers, num_input_images)
+
+    def load_imagenet(self, num_layers, num_input_images):
+        """ImageNet initialisation (reference resnet_encoder.py:40-58,70-82) from a LOCAL torchvision checkpoint
+        `resnet<num_layers>-*.pth` in $SCSFM_PRETRAINED_DIR or the torch hub cache -- there is no network to download it.
+        For the multi-image pose encoder the stem is replicated as cat([w] * n, 1) / n (resnet_encoder.py:56-57)."""
+        import glob
+        import os
+        dirs = [os.environ.get("SCSFM_PRETRAINED_DIR", ""), os.path.join(torch.hub.get_dir(), "checkpoints")]
+        hits = [f for d in dirs if d for f in sorted(glob.glob(os.path.join(d, "resnet%d-*.pth" % num_layers)))]
+        if not hits:
+            raise FileNotFoundError("no local ImageNet checkpoint resnet%d-*.pth in %s (no network access: put the torchvision "
+                                    "file there, or use pretrained=False / --with-pretrain 0)" % (num_layers, [d for d in dirs if d]))
+        sd = torch.load(hits[0], map_location="cpu")
+        if num_input_images > 1:
+            sd["conv1.weight"] = torch.cat([sd["conv1.weight"]] * num_input_images, 1) / num_input_images
+        own = self.encoder.state_dict()
+        for k, v in sd.items():
+            if k in own and own[k].shape == v.shape:
+                own[k].copy_(v)
 
 
 class _ReflConv(nn.Module):      # reference Conv3x3: keys  <name>.conv.{weight,bias}
@@ -186,6 +209,19 @@ class ArenaNet(nn.Module):
         self._hook = None          # dummy leaf that makes autograd schedule our backward
         self._pending = 0          # forward calls whose backward has not run yet (this step)
         self.grads_ready_callback = None
+        self.ctx = O.ConvCtx("fp32")   # convolution arithmetic + flipped-weight cache of THIS network (set_conv_mode)
+
+    @property
+    def conv_mode(self):
+        return self.ctx.mode
+
+    def set_conv_mode(self, mode):
+        """"fp32" (exact CUDA-core kernels), "tf32" (tcgen05, single TF32 product) or "tf32x3" (tcgen05 with
+        split-accumulate operands: fp32-level products, the parity mode on the tensor cores).  Returns self."""
+        if mode != self.ctx.mode:
+            self.ctx = O.ConvCtx(mode)
+            self._tf32_version = None          # the operand mirror holds something else in every mode
+        return self
 
     def _arena_ok(self):
         if self._flat is None:
@@ -238,9 +274,11 @@ class ArenaNet(nn.Module):
             for m in self.modules():
                 if isinstance(m, ResnetEncoder):
                     m._nbt = nbt
-        # TF32-rounded mirror of the parameter arena (refreshed at the start of every network call in tf32 mode)
+        # operand mirror of the parameter arena for the tensor-core kernels: the TF32-rounded parameters in tf32 mode, their
+        # low parts in tf32x3 mode (refreshed at the start of a network call when stale; ArenaAdam writes it with the update)
         self._flat_tf32 = torch.zeros_like(flat)
         self._tf32_version = None
+        self.ctx.invalidate()              # cached flips referred to the previous arena
         off = 0
         mods = {id(m.weight): m for m in self.modules() if isinstance(m, ConvParams)}
         for p in params:
@@ -259,17 +297,20 @@ class ArenaNet(nn.Module):
 
     def refresh_operand_weights(self):
         """Start of every network call: the weights may have changed since the last one (optimizer, load_state_dict)."""
-        if O.CONFIG["conv_mode"] == "tf32":
-            # TF32 operand mirror: ArenaAdam writes it together with the parameters (and records the arena's torch
-            # version counter); any other in-place change of the parameters bumps that counter -> re-round here
+        cx = self.ctx
+        if cx.tc:
+            # operand mirror: ArenaAdam writes it together with the parameters (and records the arena's torch
+            # version counter); any other in-place change of the parameters bumps that counter -> recompute here
             # (the shortcut is opt-in -- Trainer sets trust_adam_mirror -- because writes through `.data` are invisible to
-            # the version counters; without it the mirror is re-rounded on every call)
+            # the version counters; without it the mirror is recomputed on every call)
             if not (self.trust_adam_mirror and self._tf32_version == self._versions()):
-                O.round_tf32(self._flat, self._flat_tf32)
+                if cx.split:
+                    O.split_tf32(self._flat, self._flat_tf32)
+                else:
+                    O.round_tf32(self._flat, self._flat_tf32)
                 self._tf32_version = self._versions()
             # flipped / transposed copies for the data gradients: all of them in one launch, in place
-            lo = self._flat_tf32.data_ptr()
-            O.refresh_flips(lo, lo + 4 * self._flat_tf32.numel(), self._flat_tf32.device)
+            cx.refresh_flips(self._flat.device)
 
     def _attach_grads(self):
         """Called at the start of every backward: if an optimizer dropped the gradients
@@ -355,77 +396,77 @@ class _SumsPool:
 _SUMS = _SumsPool()
 
 
-def _bn_fwd(y, sums, bn, training, relu, residual, groups):
+def _bn_fwd(cx, y, sums, bn, training, relu, residual, groups):
     """BatchNorm over `groups` independent sample groups (one per batched network call: statistics, and the
     running-stat updates, stay per call exactly as in train.py:427-442).  num_batches_tracked of every layer is bumped
     by one add per network call (ArenaNet._nbt, see encoder_forward)."""
     return O.bn_apply(y, sums if training else None, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
-                      residual, (1 if relu else 0) | O.rnd(), groups)
+                      residual, (1 if relu else 0) | cx.rnd(), groups)
 
 
-def _conv_bn(x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
+def _conv_bn(cx, x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
     C = conv.weight.shape[0]
     sums = _SUMS.take(O.BN_SLOTS * groups * C * 2, x.device) if training else None
-    y = O.conv_fwd(x, conv.w_op(), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups)
-    z, saved = _bn_fwd(y, sums, bn, training, relu, residual, groups)
+    y = cx.conv_fwd(x, conv.w_op(cx), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups, conv.w_lo(cx))
+    z, saved = _bn_fwd(cx, y, sums, bn, training, relu, residual, groups)
     return y, z, saved
 
 
-def _conv_bn_bwd(dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None, groups=1):
+def _conv_bn_bwd(cx, dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None, groups=1):
     """Backward through relu?(bn(conv(x)) [+res]).  Returns (dx or None, dres or None)."""
-    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, (1 if relu else 0) | O.rnd(), want_dres, groups)
-    O.conv_wgrad(x, dy, ArenaNet.g(conv.weight), None, stride, pad, O.PAD_ZERO)
-    dx = O.conv_dgrad(dy, conv.w_op(), x.shape, stride, pad, addend) if need_dx else None
+    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, (1 if relu else 0) | cx.rnd(), want_dres, groups)
+    cx.conv_wgrad(x, dy, ArenaNet.g(conv.weight), None, stride, pad, O.PAD_ZERO)
+    dx = cx.conv_dgrad(dy, conv.w_op(cx), x.shape, stride, pad, addend) if need_dx else None
     return dx, dres
 
 
-def block_forward(blk, x, training, G=1):
+def block_forward(cx, blk, x, training, G=1):
     r = {"x": x, "G": G}
     if blk.bottleneck:
-        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, 1, 0, training, True, None, G)
-        r["y2"], r["h2"], r["s2"] = _conv_bn(r["h1"], blk.conv2, blk.bn2, blk.stride, 1, training, True, None, G)
+        r["y1"], r["h1"], r["s1"] = _conv_bn(cx, x, blk.conv1, blk.bn1, 1, 0, training, True, None, G)
+        r["y2"], r["h2"], r["s2"] = _conv_bn(cx, r["h1"], blk.conv2, blk.bn2, blk.stride, 1, training, True, None, G)
         last_in, last_conv, last_bn, key = r["h2"], blk.conv3, blk.bn3, "3"
         ls, lp = 1, 0
     else:
-        r["y1"], r["h1"], r["s1"] = _conv_bn(x, blk.conv1, blk.bn1, blk.stride, 1, training, True, None, G)
+        r["y1"], r["h1"], r["s1"] = _conv_bn(cx, x, blk.conv1, blk.bn1, blk.stride, 1, training, True, None, G)
         last_in, last_conv, last_bn, key = r["h1"], blk.conv2, blk.bn2, "2"
         ls, lp = 1, 1
     sc = x
     if blk.downsample is not None:
-        r["yd"], sc, r["sd"] = _conv_bn(x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
+        r["yd"], sc, r["sd"] = _conv_bn(cx, x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
     C = last_conv.weight.shape[0]
     sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x.device) if training else None
-    y = O.conv_fwd(last_in, last_conv.w_op(), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G)
-    out, saved = _bn_fwd(y, sums, last_bn, training, True, sc, G)
+    y = cx.conv_fwd(last_in, last_conv.w_op(cx), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G, last_conv.w_lo(cx))
+    out, saved = _bn_fwd(cx, y, sums, last_bn, training, True, sc, G)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
     return r, out
 
 
-def block_backward(blk, r, d_out, extra_addend=None):
+def block_backward(cx, blk, r, d_out, extra_addend=None):
     """d_out: gradient w.r.t. the block output (consumed / overwritten).  extra_addend: gradient that reaches
     the block INPUT from elsewhere (decoder skip connection) -- folded into the dgrad epilogue chain.
     Returns gradient w.r.t. the block input."""
     x, G = r["x"], r["G"]
     if blk.bottleneck:
-        dh2, dres = _conv_bn_bwd(d_out, r["out"], r["y3"], r["s3"], r["h2"], blk.conv3, blk.bn3, 1, 0, True, True, True, None, G)
-        dh1, _ = _conv_bn_bwd(dh2, r["h2"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, blk.stride, 1, True, False, True, None, G)
+        dh2, dres = _conv_bn_bwd(cx, d_out, r["out"], r["y3"], r["s3"], r["h2"], blk.conv3, blk.bn3, 1, 0, True, True, True, None, G)
+        dh1, _ = _conv_bn_bwd(cx, dh2, r["h2"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, blk.stride, 1, True, False, True, None, G)
         first = (dh1, r["h1"], r["y1"], r["s1"], blk.conv1, blk.bn1, 1, 0)
     else:
-        dh1, dres = _conv_bn_bwd(d_out, r["out"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, 1, 1, True, True, True, None, G)
+        dh1, dres = _conv_bn_bwd(cx, d_out, r["out"], r["y2"], r["s2"], r["h1"], blk.conv2, blk.bn2, 1, 1, True, True, True, None, G)
         first = (dh1, r["h1"], r["y1"], r["s1"], blk.conv1, blk.bn1, blk.stride, 1)
     if blk.downsample is not None:
-        d_sc, _ = _conv_bn_bwd(dres, None, r["yd"], r["sd"], x, blk.downsample[0], blk.downsample[1], blk.stride, 0, False,
+        d_sc, _ = _conv_bn_bwd(cx, dres, None, r["yd"], r["sd"], x, blk.downsample[0], blk.downsample[1], blk.stride, 0, False,
                                False, True, extra_addend, G)
     else:
         d_sc = dres
         if extra_addend is not None:
             d_sc = d_sc + extra_addend          # not reached by ResNet-18/50 (skips feed downsample blocks)
     dz, z, y, s, conv, bn, st, pd = first
-    dx, _ = _conv_bn_bwd(dz, z, y, s, x, conv, bn, st, pd, True, False, True, d_sc, G)
+    dx, _ = _conv_bn_bwd(cx, dz, z, y, s, x, conv, bn, st, pd, True, False, True, d_sc, G)
     return dx
 
 
-def encoder_forward(enc, imgs, training, G=1):
+def encoder_forward(cx, enc, imgs, training, G=1):
     """imgs: tuple of one (DispResNet) or two (PoseResNet, channel-concatenated) NCHW image batches."""
     t = enc.encoder
     rec = {"G": G}
@@ -438,32 +479,33 @@ def encoder_forward(enc, imgs, training, G=1):
             for m in enc.modules():
                 if isinstance(m, BNParams):
                     m.num_batches_tracked += G
-    if O.CONFIG["conv_mode"] == "tf32":
+    if cx.tc:
         # 7x7 stem on the tensor cores: input channels zero-padded 3 -> 4 / 6 -> 8 (K = 49 * Cpad), weights likewise
         cpad = 4 * len(imgs)
-        x_nhwc = O.nchw_to_nhwc_pad(imgs[0], imgs[1] if len(imgs) > 1 else None, cpad)
-        w0 = O.pad_channels(t.conv1.w_khwc(), cpad)
+        x_nhwc = O.nchw_to_nhwc_pad(imgs[0], imgs[1] if len(imgs) > 1 else None, cpad, cx.operand)
+        w0 = O.pad_channels(t.conv1.w_khwc(), cpad, cx.operand)
+        w0_lo = O.pad_channels(t.conv1.w_khwc(), cpad, O.OPERAND_LO) if cx.split else None
         C = w0.shape[0]
         sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x_nhwc.device) if training else None
-        rec["y0"] = O.conv_fwd(x_nhwc, w0, None, 2, 3, O.PAD_ZERO, O.ACT_NONE, sums, G)
-        f0, rec["s0"] = _bn_fwd(rec["y0"], sums, t.bn1, training, True, None, G)
+        rec["y0"] = cx.conv_fwd(x_nhwc, w0, None, 2, 3, O.PAD_ZERO, O.ACT_NONE, sums, G, w0_lo)
+        f0, rec["s0"] = _bn_fwd(cx, rec["y0"], sums, t.bn1, training, True, None, G)
     else:
         x_nhwc = O.nchw_to_nhwc(imgs[0], imgs[1] if len(imgs) > 1 else None)
-        rec["y0"], f0, rec["s0"] = _conv_bn(x_nhwc, t.conv1, t.bn1, 2, 3, training, True, None, G)
+        rec["y0"], f0, rec["s0"] = _conv_bn(cx, x_nhwc, t.conv1, t.bn1, 2, 3, training, True, None, G)
     rec["x"] = x_nhwc
     rec["f0"] = f0
     pooled, rec["pool_idx"] = O.maxpool_fwd(f0)
     feats, blocks, x = [f0], [], pooled
     for li in range(1, 5):
         for blk in getattr(t, "layer%d" % li):
-            r, x = block_forward(blk, x, training, G)
+            r, x = block_forward(cx, blk, x, training, G)
             blocks.append((blk, r))
         feats.append(x)
     rec["blocks"], rec["feats"] = blocks, feats
     return rec, feats
 
 
-def encoder_backward(enc, rec, d_feats):
+def encoder_backward(cx, enc, rec, d_feats):
     """d_feats[i]: gradient w.r.t. feature i coming from the decoder (None if unused).  d_feats[4] is required."""
     t = enc.encoder
     blocks = rec["blocks"]
@@ -479,7 +521,7 @@ def encoder_backward(enc, rec, d_feats):
         extra = None
         if bi - 1 in ends and d_feats[ends[bi - 1]] is not None:
             extra = d_feats[ends[bi - 1]]
-        d = block_backward(blk, r, d, extra)
+        d = block_backward(cx, blk, r, d, extra)
     # d is now the gradient w.r.t. the max-pool output
     f0 = rec["f0"]
     if d_feats[0] is not None:
@@ -491,12 +533,12 @@ def encoder_backward(enc, rec, d_feats):
     x = rec["x"]
     if x.shape[-1] != t.conv1.weight.shape[1]:
         # padded-channel stem (tf32 mode): weight gradient in the padded layout, then folded into the gradient arena
-        dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | O.rnd(), False, rec["G"])
+        dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | cx.rnd(), False, rec["G"])
         dw = torch.zeros(t.conv1.weight.shape[0], t.conv1.k, t.conv1.k, x.shape[-1], device=x.device, dtype=torch.float32)
-        O.conv_wgrad(x, dy, dw, None, 2, 3, O.PAD_ZERO)
+        cx.conv_wgrad(x, dy, dw, None, 2, 3, O.PAD_ZERO)
         O.unpad_add_(ArenaNet.g(t.conv1.weight), dw)
     else:
-        _conv_bn_bwd(d_f0, f0, rec["y0"], rec["s0"], x, t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
+        _conv_bn_bwd(cx, d_f0, f0, rec["y0"], rec["s0"], x, t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -539,7 +581,8 @@ class DispResNet(ArenaNet):
         x = L.dev_f32(x, "DispResNet input")
         self.refresh_operand_weights()
         training = self.training
-        enc_rec, feats = encoder_forward(self.encoder, (x,), training, groups)
+        cx = self.ctx
+        enc_rec, feats = encoder_forward(cx, self.encoder, (x,), training, groups)
         dec = self.decoder
         rec = {"enc": enc_rec, "stages": {}}
         cur = feats[4]
@@ -547,10 +590,10 @@ class DispResNet(ArenaNet):
         for i in range(4, -1, -1):
             st = {"in0": cur}
             c0 = dec.up(i, 0)
-            st["a"] = O.conv_fwd(cur, c0.w_op(), c0.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | O.rnd())
+            st["a"] = cx.conv_fwd(cur, c0.w_op(cx), c0.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | cx.rnd(), None, 1, c0.w_lo(cx))
             st["cat"] = O.upcat_fwd(st["a"], feats[i - 1] if i > 0 else None)
             c1 = dec.up(i, 1)
-            st["b"] = O.conv_fwd(st["cat"], c1.w_op(), c1.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | O.rnd())
+            st["b"] = cx.conv_fwd(st["cat"], c1.w_op(cx), c1.bias, 1, 1, O.PAD_REFLECT, O.ACT_ELU | cx.rnd(), None, 1, c1.w_lo(cx))
             cur = st["b"]
             if i < 4 and (training or i == 0):
                 dc = dec.disp(i)
@@ -566,6 +609,7 @@ class DispResNet(ArenaNet):
     def _backward_impl(self, rec, grads):
         dec = self.decoder
         g = ArenaNet.g
+        cx = self.ctx
         d_disp = {s: gr for s, gr in zip(rec["order"], grads) if gr is not None}
         d_feats = [None] * 5
         d_b = None          # gradient w.r.t. the pre-activation of up(i,1) (after folding every consumer)
@@ -583,29 +627,29 @@ class DispResNet(ArenaNet):
                 dpad = O.head_dgrad(dpre, dc.w_khwc(), b.shape)
                 if not have:
                     d_b = torch.empty_like(b)
-                O.fold_plain(dpad, d_b, b, O.ACT_ELU | O.rnd(), accumulate=have)
+                O.fold_plain(dpad, d_b, b, O.ACT_ELU | cx.rnd(), accumulate=have)
             elif have:
-                O.act_bwd_(d_b, b, O.ACT_ELU | O.rnd())
+                O.act_bwd_(d_b, b, O.ACT_ELU | cx.rnd())
             else:
                 continue            # nothing reaches this stage (cannot happen: stage 0 always has scale 0)
             # up(i,1): b = ELU(conv(reflect_pad(cat)))
             c1 = dec.up(i, 1)
-            O.conv_wgrad(st["cat"], d_b, g(c1.weight), c1.bias.grad, 1, 1, O.PAD_REFLECT)
-            dpad = O.conv_dgrad(d_b, c1.w_op(), st["cat"].shape, 1, 1, None, padded_input=True)
-            d_a, d_skip = O.fold_upcat(dpad, st["a"].shape[-1], st["a"], O.ACT_ELU | O.rnd())
+            cx.conv_wgrad(st["cat"], d_b, g(c1.weight), c1.bias.grad, 1, 1, O.PAD_REFLECT)
+            dpad = cx.conv_dgrad(d_b, c1.w_op(cx), st["cat"].shape, 1, 1, None, padded_input=True)
+            d_a, d_skip = O.fold_upcat(dpad, st["a"].shape[-1], st["a"], O.ACT_ELU | cx.rnd())
             if i > 0:
                 d_feats[i - 1] = d_skip
             # up(i,0): a = ELU(conv(reflect_pad(in0)))
             c0 = dec.up(i, 0)
-            O.conv_wgrad(st["in0"], d_a, g(c0.weight), c0.bias.grad, 1, 1, O.PAD_REFLECT)
-            dpad = O.conv_dgrad(d_a, c0.w_op(), st["in0"].shape, 1, 1, None, padded_input=True)
+            cx.conv_wgrad(st["in0"], d_a, g(c0.weight), c0.bias.grad, 1, 1, O.PAD_REFLECT)
+            dpad = cx.conv_dgrad(d_a, c0.w_op(cx), st["in0"].shape, 1, 1, None, padded_input=True)
             d_in = torch.empty_like(st["in0"])
             O.fold_plain(dpad, d_in, None, O.ACT_NONE, accumulate=False)
             if i < 4:
                 pending = d_in          # = raw gradient of b_{i+1}; ELU' applied once all consumers are in
             else:
                 d_feats[4] = d_in
-        encoder_backward(self.encoder, rec["enc"], d_feats)
+        encoder_backward(cx, self.encoder, rec["enc"], d_feats)
 
 
 class PoseResNet(ArenaNet):
@@ -639,26 +683,28 @@ class PoseResNet(ArenaNet):
         from . import lib as L
         img1, img2 = L.dev_f32(img1, "PoseResNet input"), L.dev_f32(img2, "PoseResNet input")
         self.refresh_operand_weights()
-        enc_rec, feats = encoder_forward(self.encoder, (img1, img2), self.training, groups)
+        cx = self.ctx
+        enc_rec, feats = encoder_forward(cx, self.encoder, (img1, img2), self.training, groups)
         n = self.decoder.net
         rec = {"enc": enc_rec, "f4": feats[4]}
-        rec["s"] = O.conv_fwd(feats[4], n[0].w_op(), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU | O.rnd())
-        rec["p0"] = O.conv_fwd(rec["s"], n[1].w_op(), n[1].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | O.rnd())
-        rec["p1"] = O.conv_fwd(rec["p0"], n[2].w_op(), n[2].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | O.rnd())
-        rec["p2"] = O.conv_fwd(rec["p1"], n[3].w_op(), n[3].bias, 1, 0, O.PAD_ZERO, O.ACT_NONE)
+        rec["s"] = cx.conv_fwd(feats[4], n[0].w_op(cx), n[0].bias, 1, 0, O.PAD_ZERO, O.ACT_RELU | cx.rnd(), None, 1, n[0].w_lo(cx))
+        rec["p0"] = cx.conv_fwd(rec["s"], n[1].w_op(cx), n[1].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | cx.rnd(), None, 1, n[1].w_lo(cx))
+        rec["p1"] = cx.conv_fwd(rec["p0"], n[2].w_op(cx), n[2].bias, 1, 1, O.PAD_ZERO, O.ACT_RELU | cx.rnd(), None, 1, n[2].w_lo(cx))
+        rec["p2"] = cx.conv_fwd(rec["p1"], n[3].w_op(cx), n[3].bias, 1, 0, O.PAD_ZERO, O.ACT_NONE, None, 1, n[3].w_lo(cx))
         return rec, [O.spatial_mean_fwd(rec["p2"], 0.01)]
 
     def _backward_impl(self, rec, grads):
         n = self.decoder.net
         g = ArenaNet.g
+        cx = self.ctx
         d = O.spatial_mean_bwd(grads[0], rec["p2"].shape, 0.01)
         chain = [(n[3], rec["p1"], 0), (n[2], rec["p0"], 1), (n[1], rec["s"], 1), (n[0], rec["f4"], 0)]
         for k, (conv, inp, pad) in enumerate(chain):
-            O.conv_wgrad(inp, d, g(conv.weight), conv.bias.grad, 1, pad, O.PAD_ZERO)
-            d = O.conv_dgrad(d, conv.w_op(), inp.shape, 1, pad)
+            cx.conv_wgrad(inp, d, g(conv.weight), conv.bias.grad, 1, pad, O.PAD_ZERO)
+            d = cx.conv_dgrad(d, conv.w_op(cx), inp.shape, 1, pad)
             if k < 3:
-                O.act_bwd_(d, inp, O.ACT_RELU | O.rnd())       # inp is the ReLU output of the previous conv
-        encoder_backward(self.encoder, rec["enc"], [None, None, None, None, d])
+                O.act_bwd_(d, inp, O.ACT_RELU | cx.rnd())       # inp is the ReLU output of the previous conv
+        encoder_backward(cx, self.encoder, rec["enc"], [None, None, None, None, d])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -668,7 +714,8 @@ class ArenaAdam:
     """torch.optim.Adam semantics (betas, eps 1e-8, weight decay folded into the gradient) with one kernel
     launch per network.  Parameters whose gradient stays zero (the unused fc head and, with
     --num-scales 1, the scale 1-3 disparity heads) are left unchanged exactly as Adam skips
-    `grad is None` parameters in the reference.  The step counter lives on the device so that the whole
+    `grad is None` parameters in the reference -- for weight_decay == 0 (the reference's scripts); with
+    weight_decay > 0 the whole arena is decayed, those unused tensors included (documented deviation).  The step counter lives on the device so that the whole
     training step can be captured in a CUDA graph."""
 
     def __init__(self, nets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
@@ -699,10 +746,12 @@ class ArenaAdam:
         self._ensure_state()
         self._step += 1
         for n in self.nets:
+            n._pending = 0     # nothing may be pending after the update (a forward whose backward never ran must not block
+            #                    the next step's gradient all-reduce; Trainer additionally checks that both were issued)
             m, v, _ = self.state[id(n)]
-            mirror = n._flat_tf32 if O.CONFIG["conv_mode"] == "tf32" else None
+            mirror = n._flat_tf32 if n.ctx.tc else None
             O.adam_step(n._flat, n._flat_grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                        0, self._step, mirror)
+                        0, self._step, mirror, O.OPERAND_LO if n.ctx.split else O.OPERAND_TF32)
             # the kernel writes through raw pointers (no torch version bump): with the mirror written the arena is in sync,
             # without it the next network call must re-round
             n._tf32_version = n._versions() if mirror is not None else None

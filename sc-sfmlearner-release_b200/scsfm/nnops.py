@@ -13,17 +13,33 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_DISP = 0, 1, 2, 3
 BN_SLOTS = 16      # SCSFM_BN_SLOTS: replicas of the fused BatchNorm sums
 ROUND_TF32 = 0x100  # SCSFM_ROUND_TF32: store the result rounded to TF32 (operand of a tensor-core conv)
+OPERAND_TF32, OPERAND_RAW, OPERAND_LO = 0, 1, 2      # SCSFM_OPERAND_*
 
-# "fp32": exact CUDA-core kernels everywhere (parity mode).  "tf32": tcgen05 tensor-core kernels on the
-# layers they support (same arithmetic class as the reference's cuDNN TF32 default on GPU).
-CONFIG = {"conv_mode": "fp32"}
+# Arithmetic of the convolutions (a property of each network, see ConvCtx -- there is no process-global mode):
+#   "fp32"    exact CUDA-core kernels everywhere
+#   "tf32"    tcgen05 tensor-core kernels, single TF32 product (the reference's cuDNN default on a GPU; ~1e-3 per layer)
+#   "tf32x3"  tcgen05 kernels with split-accumulate operands: hi*hi + lo*hi + hi*lo into the same TMEM accumulator
+#             (fp32-level products; the 1e-4 parity mode on the tensor cores)
+MODES = ("fp32", "tf32", "tf32x3")
+
+
+def tune(no_tma=0, mt=0, tw_log2=0, bn=0, wgrad=0):
+    """ScsfmConv.tune word (include/scsfm.h): per-call experiment knobs of the tensor-core kernels."""
+    t = 1 if no_tma else 0
+    t |= (mt & 3) << 4
+    t |= ((tw_log2 - 2 if tw_log2 else 0) & 3) << 6
+    t |= {0: 0, 16: 1, 32: 2, 64: 3, 128: 4}[bn] << 8
+    t |= (wgrad & 3) << 12
+    return t
 
 
 class Conv(ctypes.Structure):
     _fields_ = ([(n, ctypes.c_void_p) for n in ("inp", "w", "bias", "out", "dout", "din", "addend", "dw", "dbias",
                                                 "bn_sums")] +
                 [(n, ctypes.c_int) for n in ("bn_groups", "B", "Hi", "Wi", "Cin", "Ho", "Wo", "Cout", "kh", "kw",
-                                             "stride", "pad", "pad_mode", "act")])
+                                             "stride", "pad", "pad_mode", "act")] +
+                [(n, ctypes.c_void_p) for n in ("in_lo", "w_lo", "dout_lo")] +
+                [("tune", ctypes.c_uint), ("debug", ctypes.c_void_p)])
 
 
 _bound = False
@@ -37,22 +53,19 @@ def _lib():
         CP = ctypes.POINTER(Conv)
         for name in ("scsfm_conv2d_fwd_simt", "scsfm_conv2d_dgrad_simt", "scsfm_conv2d_wgrad_simt",
                      "scsfm_conv2d_fwd_tc", "scsfm_conv2d_dgrad_tc", "scsfm_conv2d_wgrad_tc"):
-            if hasattr(lib, name):
-                getattr(lib, name).argtypes = [CP, P]
+            getattr(lib, name).argtypes = [CP, P]
         lib.scsfm_round_tf32.argtypes = [P, P, LL, P]
-        lib.scsfm_conv_tma_config.argtypes = [I, I, I, I]
-        lib.scsfm_wgrad_config.argtypes = [I]
-        if hasattr(lib, "scsfm_weight_flip"):
-            lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, P]
-            lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, P]
-            lib.scsfm_weight_flip_batched.argtypes = [P, I, I, P]
+        lib.scsfm_split_tf32.argtypes = [P, P, LL, P]
+        lib.scsfm_weight_flip.argtypes = [P, I, I, I, I, P, I, P]
+        lib.scsfm_weight_flip_s2.argtypes = [P, I, I, I, I, I, P, I, P]
+        lib.scsfm_weight_flip_batched.argtypes = [P, I, I, P]
         lib.scsfm_nchw_to_nhwc.argtypes = [P, P, I, I, I, I, P, P]
         lib.scsfm_nhwc_to_nchw.argtypes = [P, I, I, I, I, P, P]
         lib.scsfm_head_conv_fwd.argtypes = [P, P, P, P, I, I, I, I, I, P]
         lib.scsfm_head_conv_wgrad.argtypes = [P, P, P, P, I, I, I, I, P]
         lib.scsfm_head_conv_dgrad.argtypes = [P, P, P, I, I, I, I, P]
-        lib.scsfm_nchw_to_nhwc_pad.argtypes = [P, P, I, I, I, I, I, P, P]
-        lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, P]
+        lib.scsfm_nchw_to_nhwc_pad.argtypes = [P, P, I, I, I, I, I, P, I, P]
+        lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, I, P]
         lib.scsfm_unpad_add.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
         lib.scsfm_bn_apply.argtypes = [P, P, P, P, P, P, F, F, P, P, P, LL, I, I, I, P]
@@ -64,39 +77,35 @@ def _lib():
         lib.scsfm_act_bwd.argtypes = [P, P, LL, I, P]
         lib.scsfm_spatial_mean_fwd.argtypes = [P, I, I, I, F, P, P]
         lib.scsfm_spatial_mean_bwd.argtypes = [P, I, I, I, F, P, P]
-        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P, P]
+        lib.scsfm_adam_step.argtypes = [P, P, P, P, LL, F, F, F, F, F, I, P, P, I, P]
         _bound = True
     return lib
-
-
-def conv_tma_config(enable=1, force_mt=0, force_bn=0, force_tw_log2=0):
-    """Experiment hook of the TMA halo-patch convolution kernel (see include/scsfm.h)."""
-    L.check(_lib().scsfm_conv_tma_config(enable, force_mt, force_bn, force_tw_log2), "scsfm_conv_tma_config")
-
-
-def wgrad_config(wide):
-    """Experiment hook: select the wide weight-gradient kernel (see include/scsfm.h)."""
-    L.check(_lib().scsfm_wgrad_config(int(wide)), "scsfm_wgrad_config")
-
-
-def rnd():
-    """Flag to OR into act / relu arguments of kernels whose output feeds a tensor-core convolution."""
-    return ROUND_TF32 if CONFIG["conv_mode"] == "tf32" else 0
 
 
 def round_tf32(src, dst):
     L.launch(_lib().scsfm_round_tf32, "scsfm_round_tf32", "weight_round", 1, 8.0 * src.numel(), L.ptr(src), L.ptr(dst), src.numel(), L.stream())
 
 
+def split_tf32(src, dst=None):
+    """Low part of a split-accumulate operand: dst = tf32(src - trunc_tf32(src)) (ScsfmConv.in_lo / w_lo / dout_lo)."""
+    if dst is None:
+        dst = torch.empty_like(src)
+    L.launch(_lib().scsfm_split_tf32, "scsfm_split_tf32", "split", 1, 8.0 * src.numel(), L.ptr(src), L.ptr(dst), src.numel(), L.stream())
+    return dst
+
+
+def lo_of(t):
+    """Low part of tensor `t`, computed once per tensor object (activations and gradients are written once and then only
+    read as convolution operands; the cache lives on the tensor object and dies with it)."""
+    lo = getattr(t, "_scsfm_lo", None)
+    if lo is None:
+        lo = split_tf32(t)
+        t._scsfm_lo = lo
+    return lo
+
+
 def empty(shape, like):
     return torch.empty(shape, device=like.device, dtype=torch.float32)
-
-
-def _use_tc(kind, Cin, Cout, kh, stride):
-    if CONFIG["conv_mode"] != "tf32":
-        return False
-    lib = _lib()
-    return hasattr(lib, "scsfm_conv2d_%s_tc" % kind) and tc_supported(kind, Cin, Cout, kh, stride)
 
 
 def tc_supported(kind, Cin, Cout, kh, stride):
@@ -108,10 +117,6 @@ def tc_supported(kind, Cin, Cout, kh, stride):
     if kind == "wgrad":
         return Cin % 4 == 0 and Cout % 4 == 0 and Cout >= 16
     return False
-
-
-_flip_cache = {}          # (weight pointer, shape, stride, pad) -> flipped weights (persistent buffers)
-_flip_tables = []         # live FlipTable objects (one per network arena)
 
 
 def _s2_classes(kh, kw, pad):
@@ -130,65 +135,25 @@ def _s2_classes(kh, kw, pad):
     return out
 
 
-def flipped_weights(w, stride=1, pad=0):
-    """[Cout,kh,kw,Cin] -> weights of the transposed conv ([Cin,kh,kw,Cout], reversed taps; for stride 2 the four
-    parity-class tap subsets back to back), TF32-rounded.  Cached per weight tensor; the cache entry is refreshed in
-    place by refresh_flips() (one launch per network and step) or dropped by invalidate_weight_cache()."""
-    key = (w.data_ptr(), tuple(w.shape), stride, pad)
-    wt = _flip_cache.get(key)
-    if wt is None:
-        Cout, kh, kw, Cin = w.shape
-        wt = empty((Cin, kh, kw, Cout), w)
-        if stride == 1:
-            L.launch(_lib().scsfm_weight_flip, "scsfm_weight_flip", "weight_flip", 1, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw, Cin,
-                     L.ptr(wt), L.stream())
-        else:
-            L.launch(_lib().scsfm_weight_flip_s2, "scsfm_weight_flip_s2", "weight_flip", 4, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw,
-                     Cin, pad, L.ptr(wt), L.stream())
-        _flip_cache[key] = wt
-    return wt
-
-
 class FlipTable:
-    """Device job table of every cached flip whose source weights live in [lo, hi) (one network's operand arena)."""
+    """Device job table of every cached flip of one context (one network's operand arena)."""
 
-    def __init__(self, lo, hi, device):
-        self.lo, self.hi = lo, hi
-        self.keys = sorted(k for k in _flip_cache if lo <= k[0] < hi)
+    def __init__(self, cache, device):
+        self.keys = sorted(cache)
         rows, blk = [], 0
         for key in self.keys:
-            ptr, (Cout, kh, kw, Cin), stride, pad = key
-            dst = _flip_cache[key].data_ptr()
+            ptr, (Cout, kh, kw, Cin), stride, pad, operand = key
+            dst = cache[key][1].data_ptr()
             jobs = [(kh, kw, kh - 1, kw - 1)] if stride == 1 else _s2_classes(kh, kw, pad)
             for (jh, jw, dy_max, dx_max) in jobs:
                 total = Cout * jh * jw * Cin
                 if total > 0:
-                    rows.append([ptr, dst, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, stride, blk])
+                    rows.append([ptr, dst, Cout, kh, kw, Cin, jh, jw, dy_max, dx_max, stride | (operand << 8), blk])
                     blk += ((Cout + 31) // 32) * ((Cin + 31) // 32) * jh * jw      # one block per 32x32 tile of one tap
                 dst += 4 * total
-        self.n_rows, self.total_blocks, self.bytes = len(rows), blk, 8.0 * sum(_flip_cache[k].numel() for k in self.keys)
+        self.n_rows, self.total_blocks, self.bytes = len(rows), blk, 8.0 * sum(cache[k][1].numel() for k in self.keys)
         rows.append([0] * 11 + [blk])
         self.table = torch.tensor(rows, dtype=torch.int64).to(device)
-
-
-def refresh_flips(lo, hi, device):
-    """The weights in [lo, hi) have changed: recompute every cached flip of them with one launch."""
-    keys = sorted(k for k in _flip_cache if lo <= k[0] < hi)
-    if not keys:
-        return
-    tab = next((t for t in _flip_tables if t.lo == lo and t.hi == hi), None)
-    if tab is None or tab.keys != keys:
-        if tab is not None:
-            _flip_tables.remove(tab)
-        tab = FlipTable(lo, hi, device)
-        _flip_tables.append(tab)
-    L.launch(_lib().scsfm_weight_flip_batched, "scsfm_weight_flip_batched", "weight_flip", 1, tab.bytes, L.ptr(tab.table), tab.n_rows,
-             tab.total_blocks, L.stream())
-
-
-def invalidate_weight_cache():
-    _flip_cache.clear()
-    del _flip_tables[:]
 
 
 def conv_desc(x_shape, w, stride, pad, pad_mode, act):
@@ -197,7 +162,7 @@ def conv_desc(x_shape, w, stride, pad, pad_mode, act):
     Ho = (Hi + 2 * pad - kh) // stride + 1
     Wo = (Wi + 2 * pad - kw) // stride + 1
     return Conv(None, L.ptr(w), None, None, None, None, None, None, None, None, 1, B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw,
-                stride, pad, pad_mode, act)
+                stride, pad, pad_mode, act, None, None, None, 0, None)
 
 
 def _tag(d):
@@ -210,52 +175,141 @@ def _flops(d):
     return 2.0 * d.B * d.Ho * d.Wo * d.Cout * d.kh * d.kw * d.Cin
 
 
-def conv_fwd(x, w, bias=None, stride=1, pad=0, pad_mode=PAD_ZERO, act=ACT_NONE, bn_sums=None, bn_groups=1):
-    """y = act(conv(x, w) + bias); optionally accumulates per-(group, channel) sum / sum-of-squares of y."""
-    lib = _lib()
-    d = conv_desc(x.shape, w, stride, pad, pad_mode, act)
-    y = empty((d.B, d.Ho, d.Wo, d.Cout), x)
-    d.inp, d.bias, d.out, d.bn_sums, d.bn_groups = x.data_ptr(), bias.data_ptr() if bias is not None else None, \
-        y.data_ptr(), bn_sums.data_ptr() if bn_sums is not None else None, bn_groups
-    tc = _use_tc("fwd", d.Cin, d.Cout, d.kh, stride)
-    _tag(d)
-    fn = lib.scsfm_conv2d_fwd_tc if tc else lib.scsfm_conv2d_fwd_simt
-    L.launch(fn, "scsfm_conv2d_fwd", "conv_fwd_tc" if tc else "conv_fwd_simt", 1, _flops(d), ctypes.byref(d), L.stream())
-    return y
+class ConvCtx:
+    """Convolution context of ONE network: arithmetic mode, experiment knobs and the cache of flipped / transposed
+    data-gradient weights.  Everything the convolution entry points need beyond their tensor arguments lives here (and
+    travels to the C library inside the ScsfmConv descriptor), not in module-level state."""
 
+    def __init__(self, mode="fp32"):
+        if mode not in MODES:
+            raise ValueError("conv mode must be one of %s, got %r" % (MODES, mode))
+        self.mode = mode
+        self.tune = 0                 # ScsfmConv.tune of every call made through this context (see tune())
+        self.debug = None             # ScsfmConv.debug: uint64 tensor [8 * SMs] of per-role cycle counters, or None
+        self._flips = {}              # (source pointer, shape, stride, pad, operand) -> (source tensor, flipped weights)
+        self._table = None
 
-def conv_dgrad(dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=False):
-    """Gradient w.r.t. the conv input.  padded_input=True returns the gradient of the reflect-PADDED input
-    ([B,H+2,W+2,C], to be folded by fold_bwd) for a pad-1 reflection conv."""
-    lib = _lib()
-    B, Hi, Wi, Cin = x_shape
-    if padded_input:
-        Hi, Wi, pad = Hi + 2, Wi + 2, 0
-    d = conv_desc((B, Hi, Wi, Cin), w, stride, pad, PAD_ZERO, ACT_NONE)
-    assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:]), (d.Ho, d.Wo, d.Cout, dout.shape)
-    din = empty((B, Hi, Wi, Cin), dout)
-    d.dout, d.din, d.addend = dout.data_ptr(), din.data_ptr(), addend.data_ptr() if addend is not None else None
-    tc = _use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
-    _tag(d)
-    if tc:
-        d.w = flipped_weights(w, stride, pad).data_ptr()
-    fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
-    L.launch(fn, "scsfm_conv2d_dgrad", "conv_dgrad_tc" if tc else "conv_dgrad_simt", 1, _flops(d), ctypes.byref(d), L.stream())
-    return din
+    # -- mode -----------------------------------------------------------------------------------------
+    @property
+    def tc(self):
+        return self.mode != "fp32"
 
+    @property
+    def split(self):
+        return self.mode == "tf32x3"
 
-def conv_wgrad(x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
-    """dw += dout^T * gather(x); dbias += column sums of dout."""
-    lib = _lib()
-    d = conv_desc(x.shape, dw, stride, pad, pad_mode, ACT_NONE)
-    assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:])
-    d.inp, d.dout, d.dw, d.dbias = x.data_ptr(), dout.data_ptr(), dw.data_ptr(), dbias.data_ptr() if dbias is not None else None
-    d.w = None
-    tc = _use_tc("wgrad", d.Cin, d.Cout, d.kh, stride)
-    _tag(d)
-    fn = lib.scsfm_conv2d_wgrad_tc if tc else lib.scsfm_conv2d_wgrad_simt
-    L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
-             ctypes.byref(d), L.stream())
+    def rnd(self):
+        """Flag to OR into act / relu arguments of kernels whose output feeds a single-product TF32 convolution."""
+        return ROUND_TF32 if self.mode == "tf32" else 0
+
+    @property
+    def operand(self):
+        """SCSFM_OPERAND_* of tensors prepared for the tensor cores (padded stem input / weights)."""
+        return OPERAND_TF32 if self.mode == "tf32" else OPERAND_RAW
+
+    def _use_tc(self, kind, Cin, Cout, kh, stride):
+        return self.tc and tc_supported(kind, Cin, Cout, kh, stride)
+
+    def _finish(self, d):
+        d.tune = self.tune
+        d.debug = self.debug.data_ptr() if self.debug is not None else None
+
+    # -- flipped weights of the data gradients -----------------------------------------------------------
+    def flipped_weights(self, w, stride, pad, operand):
+        """[Cout,kh,kw,Cin] -> weights of the transposed conv ([Cin,kh,kw,Cout], reversed taps; for stride 2 the four
+        parity-class tap subsets back to back) as operand kind `operand`.  Cached per source tensor (the entry keeps the
+        source alive, so its address cannot be recycled while the entry exists); refreshed in place by refresh_flips()."""
+        key = (w.data_ptr(), tuple(w.shape), stride, pad, operand)
+        hit = self._flips.get(key)
+        if hit is None:
+            Cout, kh, kw, Cin = w.shape
+            wt = empty((Cin, kh, kw, Cout), w)
+            if stride == 1:
+                L.launch(_lib().scsfm_weight_flip, "scsfm_weight_flip", "weight_flip", 1, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw, Cin,
+                         L.ptr(wt), operand, L.stream())
+            else:
+                L.launch(_lib().scsfm_weight_flip_s2, "scsfm_weight_flip_s2", "weight_flip", 4, 8.0 * w.numel(), L.ptr(w), Cout, kh, kw,
+                         Cin, pad, L.ptr(wt), operand, L.stream())
+            hit = self._flips[key] = (w, wt)
+            self._table = None
+        return hit[1]
+
+    def refresh_flips(self, device):
+        """The source weights have changed (optimizer step): recompute every cached flip with one launch."""
+        if not self._flips:
+            return
+        if self._table is None:
+            self._table = FlipTable(self._flips, device)
+        tab = self._table
+        L.launch(_lib().scsfm_weight_flip_batched, "scsfm_weight_flip_batched", "weight_flip", 1, tab.bytes, L.ptr(tab.table), tab.n_rows,
+                 tab.total_blocks, L.stream())
+
+    def invalidate(self):
+        self._flips.clear()
+        self._table = None
+
+    # -- convolutions ---------------------------------------------------------------------------------------
+    def conv_fwd(self, x, w, bias=None, stride=1, pad=0, pad_mode=PAD_ZERO, act=ACT_NONE, bn_sums=None, bn_groups=1, w_lo=None):
+        """y = act(conv(x, w) + bias); optionally accumulates per-(group, channel) sum / sum-of-squares of y.
+        w_lo: low part of the weights (tf32x3 mode)."""
+        lib = _lib()
+        d = conv_desc(x.shape, w, stride, pad, pad_mode, act)
+        y = empty((d.B, d.Ho, d.Wo, d.Cout), x)
+        d.inp, d.bias, d.out, d.bn_sums, d.bn_groups = x.data_ptr(), bias.data_ptr() if bias is not None else None, \
+            y.data_ptr(), bn_sums.data_ptr() if bn_sums is not None else None, bn_groups
+        tc = self._use_tc("fwd", d.Cin, d.Cout, d.kh, stride)
+        if tc and self.split:
+            if w_lo is None:
+                raise RuntimeError("tf32x3 convolution called without the low part of its weights")
+            d.in_lo, d.w_lo = lo_of(x).data_ptr(), w_lo.data_ptr()
+        self._finish(d)
+        _tag(d)
+        fn = lib.scsfm_conv2d_fwd_tc if tc else lib.scsfm_conv2d_fwd_simt
+        L.launch(fn, "scsfm_conv2d_fwd", "conv_fwd_tc" if tc else "conv_fwd_simt", 1, _flops(d), ctypes.byref(d), L.stream())
+        return y
+
+    def conv_dgrad(self, dout, w, x_shape, stride=1, pad=0, addend=None, padded_input=False, w_src=None):
+        """Gradient w.r.t. the conv input.  padded_input=True returns the gradient of the reflect-PADDED input
+        ([B,H+2,W+2,C], to be folded by fold_bwd) for a pad-1 reflection conv.  w: the forward operand weights
+        [Cout,kh,kw,Cin]; w_src (tf32x3): the raw weights both flipped parts are derived from (defaults to w)."""
+        lib = _lib()
+        B, Hi, Wi, Cin = x_shape
+        if padded_input:
+            Hi, Wi, pad = Hi + 2, Wi + 2, 0
+        d = conv_desc((B, Hi, Wi, Cin), w, stride, pad, PAD_ZERO, ACT_NONE)
+        assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:]), (d.Ho, d.Wo, d.Cout, dout.shape)
+        din = empty((B, Hi, Wi, Cin), dout)
+        d.dout, d.din, d.addend = dout.data_ptr(), din.data_ptr(), addend.data_ptr() if addend is not None else None
+        tc = self._use_tc("dgrad", d.Cin, d.Cout, d.kh, stride)
+        if tc:
+            if self.split:
+                src = w if w_src is None else w_src
+                d.w = self.flipped_weights(src, stride, pad, OPERAND_RAW).data_ptr()
+                d.w_lo = self.flipped_weights(src, stride, pad, OPERAND_LO).data_ptr()
+                d.dout_lo = lo_of(dout).data_ptr()
+            else:
+                d.w = self.flipped_weights(w, stride, pad, OPERAND_TF32).data_ptr()
+        self._finish(d)
+        _tag(d)
+        fn = lib.scsfm_conv2d_dgrad_tc if tc else lib.scsfm_conv2d_dgrad_simt
+        L.launch(fn, "scsfm_conv2d_dgrad", "conv_dgrad_tc" if tc else "conv_dgrad_simt", 1, _flops(d), ctypes.byref(d), L.stream())
+        return din
+
+    def conv_wgrad(self, x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
+        """dw += dout^T * gather(x); dbias += column sums of dout."""
+        lib = _lib()
+        d = conv_desc(x.shape, dw, stride, pad, pad_mode, ACT_NONE)
+        assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:])
+        d.inp, d.dout, d.dw, d.dbias = x.data_ptr(), dout.data_ptr(), dw.data_ptr(), dbias.data_ptr() if dbias is not None else None
+        d.w = None
+        tc = self._use_tc("wgrad", d.Cin, d.Cout, d.kh, stride)
+        if tc and self.split:
+            d.in_lo, d.dout_lo = lo_of(x).data_ptr(), lo_of(dout).data_ptr()
+        self._finish(d)
+        _tag(d)
+        fn = lib.scsfm_conv2d_wgrad_tc if tc else lib.scsfm_conv2d_wgrad_simt
+        L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
+                 ctypes.byref(d), L.stream())
 
 
 def head_fwd(x, w, bias, act):
@@ -289,20 +343,20 @@ def nchw_to_nhwc(a, b=None):
     return out
 
 
-def nchw_to_nhwc_pad(a, b, Cpad):
+def nchw_to_nhwc_pad(a, b, Cpad, operand=OPERAND_TF32):
     B, C, H, W = a.shape
     out = empty((B, H, W, Cpad), a)
     L.launch(_lib().scsfm_nchw_to_nhwc_pad, "scsfm_nchw_to_nhwc_pad", "layout", 1, 8.0 * out.numel(), L.ptr(a), L.ptr(b), B, C, H, W, Cpad,
-             L.ptr(out), L.stream())
+             L.ptr(out), operand, L.stream())
     return out
 
 
-def pad_channels(w, Cpad):
-    """[..., C] -> [..., Cpad] zero padded, TF32 rounded (stem weights)."""
+def pad_channels(w, Cpad, operand=OPERAND_TF32):
+    """[..., C] -> [..., Cpad] zero padded, as operand kind `operand` (stem weights)."""
     C = w.shape[-1]
     out = empty(tuple(w.shape[:-1]) + (Cpad,), w)
     L.launch(_lib().scsfm_pad_channels, "scsfm_pad_channels", "weight_round", 1, 8.0 * out.numel(), L.ptr(w), w.numel() // C, C, Cpad,
-             L.ptr(out), L.stream())
+             L.ptr(out), operand, L.stream())
     return out
 
 
@@ -410,7 +464,8 @@ def spatial_mean_bwd(dout, x_shape, scale):
     return dx
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, step_dev=None, param_tf32=None):
-    L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, (32.0 if param_tf32 is not None else 28.0) * param.numel(), L.ptr(param),
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, step_dev=None, mirror=None,
+              mirror_operand=OPERAND_TF32):
+    L.launch(_lib().scsfm_adam_step, "scsfm_adam_step", "adam", 1, (32.0 if mirror is not None else 28.0) * param.numel(), L.ptr(param),
              L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, weight_decay, step, L.ptr(step_dev),
-             L.ptr(param_tf32), L.stream())
+             L.ptr(mirror), mirror_operand, L.stream())

@@ -33,8 +33,11 @@ class Trainer:
     """Holds the two networks, the fused Adam and (optionally) the data-parallel gradient exchange."""
 
     def __init__(self, disp_net, pose_net, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.0, num_scales=1, with_ssim=1,
-                 with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None):
+                 with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None, conv_mode=None):
         self.disp_net, self.pose_net = disp_net, pose_net
+        if conv_mode is not None:           # "fp32" | "tf32" | "tf32x3" (nnops.MODES); None keeps each network's own setting
+            disp_net.set_conv_mode(conv_mode)
+            pose_net.set_conv_mode(conv_mode)
         self.optimizer = ArenaAdam([disp_net, pose_net], lr=lr, betas=betas, weight_decay=weight_decay)
         for n in (disp_net, pose_net):
             n.trust_adam_mirror = True      # this loop changes parameters only through ArenaAdam (which writes the TF32 mirror)
@@ -113,11 +116,20 @@ class Trainer:
         self._graph = graph
         L.PROF.update(prof)
 
+    def drop_graph(self):
+        """Forget a captured graph: later steps run eagerly."""
+        self._graph = None
+        self.launches_per_step = None
+
     def _eager_step(self, tgt_img, ref_imgs, intrinsics):
         loss, photo, smooth, geo = self.losses(tgt_img, ref_imgs, intrinsics)
         self.optimizer.zero_grad()
         loss.backward()
         if self.exchange is not None:
+            # every network must have handed its gradient arena to the exchange (a forward whose backward never ran would
+            # leave the replicas silently diverging)
+            if self.exchange.pending() != 2:
+                raise RuntimeError("data-parallel step: %d of 2 gradient all-reduces were issued" % self.exchange.pending())
             self.exchange.wait()
         self.optimizer.step()
         return loss.detach(), photo.detach(), smooth.detach(), geo.detach()

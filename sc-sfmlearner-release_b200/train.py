@@ -56,7 +56,10 @@ parser.add_argument("-c", "--geometry-consistency-weight", type=float, help="wei
 parser.add_argument("--with-ssim", type=int, default=1, help="with ssim or not")
 parser.add_argument("--with-mask", type=int, default=1, help="with the the mask for moving objects and occlusions or not")
 parser.add_argument("--with-auto-mask", type=int, default=0, help="with the the mask for stationary points")
-parser.add_argument("--with-pretrain", type=int, default=1, help="with or without imagenet pretrain for resnet (needs network access: use 0 here)")
+parser.add_argument("--with-pretrain", type=int, default=0,
+                    help="with or without imagenet pretrain for resnet.  The reference defaults to 1 and downloads the torchvision "
+                         "weights; there is no network here, so the default is 0 and 1 loads resnet{18,50}-*.pth from "
+                         "$SCSFM_PRETRAINED_DIR or the torch hub cache (clear error if absent)")
 parser.add_argument("--dataset", type=str, choices=["kitti", "nyu"], default="kitti", help="the dataset to train")
 parser.add_argument("--pretrained-disp", dest="pretrained_disp", default=None, metavar="PATH", help="path to pre-trained dispnet model")
 parser.add_argument("--pretrained-pose", dest="pretrained_pose", default=None, metavar="PATH", help="path to pre-trained Pose net model")
@@ -64,7 +67,9 @@ parser.add_argument("--name", dest="name", type=str, required=True, help="name o
 parser.add_argument("--padding-mode", type=str, choices=["zeros", "border"], default="zeros", help="padding mode for image warping")
 parser.add_argument("--with-gt", action="store_true", help="use ground truth for validation (npy depth maps, see the reference's data/kitti_raw_loader.py)")
 # additions of this implementation
-parser.add_argument("--conv-mode", choices=["fp32", "tf32"], default="tf32", help="fp32 = exact CUDA-core convolutions (parity mode); tf32 = tcgen05 tensor cores")
+parser.add_argument("--conv-mode", choices=["fp32", "tf32", "tf32x3"], default="tf32x3",
+                    help="tf32x3 = tcgen05 tensor cores with split-accumulate operands (fp32-level results, the parity mode); tf32 = "
+                         "tcgen05 single TF32 product (cuDNN's default arithmetic, fastest); fp32 = exact CUDA-core convolutions")
 parser.add_argument("--cuda-graph", type=int, default=1, help="capture the training step in a CUDA graph (single GPU)")
 parser.add_argument("--synthetic-size", type=int, nargs=2, default=[256, 832], metavar=("H", "W"))
 
@@ -147,7 +152,6 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    nnops.CONFIG["conv_mode"] = args.conv_mode
 
     timestamp = datetime.datetime.now().strftime("%m-%d-%H:%M")
     args.save_path = os.path.join("checkpoints", args.name, timestamp)
@@ -162,8 +166,11 @@ def main():
 
     if rank == 0:
         print("=> creating model")
-    disp_net = models.DispResNet(args.resnet_layers, args.with_pretrain).to(device)
-    pose_net = models.PoseResNet(18, args.with_pretrain).to(device)      # train.py:155 hard-codes 18 for the pose net
+    try:
+        disp_net = models.DispResNet(args.resnet_layers, args.with_pretrain).to(device)
+        pose_net = models.PoseResNet(18, args.with_pretrain).to(device)      # train.py:155 hard-codes 18 for the pose net
+    except FileNotFoundError as e:
+        raise SystemExit("--with-pretrain 1: %s" % e)
     if args.pretrained_disp:
         disp_net.load_state_dict(torch.load(args.pretrained_disp, map_location=device)["state_dict"], strict=False)
     if args.pretrained_pose:
@@ -172,7 +179,7 @@ def main():
     trainer = Trainer(disp_net, pose_net, lr=args.lr, betas=(args.momentum, args.beta), weight_decay=args.weight_decay,
                       num_scales=args.num_scales, with_ssim=args.with_ssim, with_mask=args.with_mask,
                       with_auto_mask=args.with_auto_mask, padding_mode=args.padding_mode, w1=args.photo_loss_weight,
-                      w2=args.smooth_loss_weight, w3=args.geometry_consistency_weight, distributed=world > 1)
+                      w2=args.smooth_loss_weight, w3=args.geometry_consistency_weight, distributed=world > 1, conv_mode=args.conv_mode)
     if rank == 0:
         with open(os.path.join(args.save_path, args.log_summary), "w") as f:
             csv.writer(f, delimiter="\t").writerow(["train_loss", "validation_loss"])
@@ -180,6 +187,9 @@ def main():
             csv.writer(f, delimiter="\t").writerow(["train_loss", "photo_loss", "smooth_loss", "geometry_consistency_loss"])
 
     for epoch in range(args.epochs):
+        sampler = getattr(train_loader, "sampler", None)
+        if hasattr(sampler, "set_epoch"):
+            sampler.set_epoch(epoch)           # DistributedSampler: a different shuffle every epoch
         train_loss = train(args, train_loader, trainer, device, rank, world)
         if args.with_gt:
             errors, names = validate_with_gt(args, val_loader, disp_net, device)

@@ -66,14 +66,52 @@ def test_network_entry_points_reject_bad_arguments_without_a_gpu():
     from scsfm import nnops as O
     L = O._lib()
     n0 = lib.launch_count()
-    assert L.scsfm_conv_tma_config(1, 3, 0, 0) == -1 and b"conv_tma_config" in L.scsfm_last_error()
-    assert L.scsfm_conv_tma_config(1, 0, 48, 0) == -1
-    assert L.scsfm_conv_tma_config(1, 0, 0, 5) == -1
-    assert L.scsfm_conv_tma_config(1, 2, 128, 4) == 0 and L.scsfm_conv_tma_config(1, 0, 0, 0) == 0
+    assert L.scsfm_weight_flip(None, 8, 3, 3, 8, None, 5, None) == -1 and b"weight_flip" in L.scsfm_last_error()
+    assert L.scsfm_split_tf32(None, None, 16, None) == -1 and b"split_tf32" in L.scsfm_last_error()
+    assert L.scsfm_adam_step(None, None, None, None, 0, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, 0, None) == -1
     assert L.scsfm_weight_flip_batched(None, 1, 1, None) == -1
     assert L.scsfm_head_conv_dgrad(None, None, None, 1, 8, 8, 16, None) == -1
     assert L.scsfm_conv2d_fwd_tc(None, None) == -1
     assert lib.launch_count() == n0          # nothing was launched
+
+
+def test_conv_descriptor_matches_the_c_struct_and_tune_word():
+    """The ctypes mirror of ScsfmConv must have the C layout (include/scsfm.h) and nnops.tune() the SCSFM_TUNE_* encoding."""
+    import subprocess
+    import tempfile
+    from scsfm import nnops as O
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "scsfm.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ScsfmConv), offsetof(ScsfmConv, bn_groups), offsetof(ScsfmConv, act),
+           offsetof(ScsfmConv, in_lo), offsetof(ScsfmConv, tune), offsetof(ScsfmConv, debug));
+    printf("%u %u\n", SCSFM_TUNE_NO_TMA | SCSFM_TUNE_MT(2) | SCSFM_TUNE_TW(4) | SCSFM_TUNE_BN(64) | SCSFM_TUNE_WGRAD(2),
+           SCSFM_TUNE_MT(1) | SCSFM_TUNE_TW(3) | SCSFM_TUNE_BN(128));
+    return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")], text=True).split()
+    C = O.Conv
+    assert [int(v) for v in out[:6]] == [ctypes.sizeof(C), C.bn_groups.offset, C.act.offset, C.in_lo.offset, C.tune.offset, C.debug.offset]
+    assert int(out[6]) == O.tune(no_tma=1, mt=2, tw_log2=4, bn=64, wgrad=2) and int(out[7]) == O.tune(mt=1, tw_log2=3, bn=128)
+
+
+def test_conv_context_is_per_network_state():
+    """No process-global convolution mode: every network owns its ConvCtx."""
+    import models
+    from scsfm import nnops as O
+    a, b = models.DispResNet(18, False), models.PoseResNet(18, False)
+    assert a.conv_mode == b.conv_mode == "fp32"
+    a.set_conv_mode("tf32x3")
+    assert a.conv_mode == "tf32x3" and b.conv_mode == "fp32" and a.ctx.split and not b.ctx.tc
+    assert a.ctx.rnd() == 0 and O.ConvCtx("tf32").rnd() == O.ROUND_TF32
+    with pytest.raises(ValueError):
+        a.set_conv_mode("bf16")
+    assert not hasattr(O, "CONFIG")
 
 
 def test_stride2_parity_classes_partition_the_taps():

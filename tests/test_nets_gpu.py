@@ -67,7 +67,8 @@ def test_conv_fwd_dgrad_wgrad_vs_torch_fp64(case):
     wc = w.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
     bc = b.detach().float().to(DEV) if bias else None
     sums = torch.zeros(O.BN_SLOTS * Cout * 2, device=DEV, dtype=torch.float64)
-    yc = O.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1)
+    cx = O.ConvCtx("fp32")
+    yc = cx.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1)
     assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < 2e-6
     s = sums.view(O.BN_SLOTS, Cout, 2).sum(0).cpu()
     np.testing.assert_allclose(s[:, 0], y.detach().sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
@@ -76,16 +77,16 @@ def test_conv_fwd_dgrad_wgrad_vs_torch_fp64(case):
     dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
     dw = torch.zeros_like(wc)
     db = torch.zeros(Cout, device=DEV) if bias else None
-    O.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
+    cx.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
     assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 2e-6
     if bias:
         assert rel_l2(db, b.grad) < 2e-6
     if pad_mode == 0:
         add = torch.randn(B, H, W, Cin, generator=g).to(DEV)
-        dx = O.conv_dgrad(dc, wc, xc.shape, stride, pad, add)
+        dx = cx.conv_dgrad(dc, wc, xc.shape, stride, pad, add)
         assert rel_l2((dx - add).permute(0, 3, 1, 2), x.grad) < 2e-6
     else:
-        dpad = O.conv_dgrad(dc, wc, xc.shape, stride, pad, None, padded_input=True)
+        dpad = cx.conv_dgrad(dc, wc, xc.shape, stride, pad, None, padded_input=True)
         dx = torch.zeros_like(xc)
         O.fold_plain(dpad, dx, None, O.ACT_NONE, accumulate=False)
         assert rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 2e-6
@@ -152,21 +153,23 @@ def test_bn_pool_upcat_ops_vs_torch():
     assert rel_l2(d_sk.permute(0, 3, 1, 2), sk.grad) < 1e-6
 
 
-def _build(kind, layers):
+def _build(kind, layers, mode="fp32"):
     import models
     net = models.DispResNet(layers, False) if kind == "disp" else models.PoseResNet(layers, False)
     net.load_state_dict(det_weights(net.state_dict()))
-    return net.to(DEV)
+    return net.to(DEV).set_conv_mode(mode)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("layers", [18, 50])
 @pytest.mark.parametrize("kind", ["disp", "pose"])
-def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind):
-    """Train-mode forward, backward (every parameter gradient), BN running stats and eval-mode forward."""
+def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind, mode):
+    """Train-mode forward, backward (every parameter gradient), BN running stats and eval-mode forward, in both 1e-4
+    parity modes: exact CUDA-core convolutions ("fp32") and split-accumulate tcgen05 convolutions ("tf32x3")."""
     from oracle import nets as N
     g = golden_nets
     tag = f"{kind}{layers}"
-    net = _build(kind, layers)
+    net = _build(kind, layers, mode)
     sd = net.state_dict()
     assert list(sd.keys()) == list(g[f"{tag}_keys"])
     net.train()
@@ -209,7 +212,7 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind):
     errs = sorted((rel_l2(grads[k], gr), k) for k, gr in g64.items())
     errs_ref = sorted(rel_l2(g32[k], gr) for k, gr in g64.items())
     med, worst = errs[len(errs) // 2][0], errs[-1]
-    print(tag, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle's own: median %.2e worst %.2e"
+    print(tag, mode, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle's own: median %.2e worst %.2e"
           % (med, worst[0], worst[1], errs_ref[len(errs_ref) // 2], errs_ref[-1]))
     # systematic accuracy = the median (must be fp32-noise level); individual parameters may see a ReLU/ELU gate flip on an
     # activation that is ~0 in one evaluation and ~-0 in the other (any independent fp32 evaluation does), hence the looser worst bound
@@ -301,22 +304,26 @@ TC_CASES = [
 ]
 
 
-# (enable, force_mt, force_bn, force_tw_log2) of scsfm_conv_tma_config: the heuristic, the cp.async gather kernel alone,
-# and two forced tilings of the persistent TMA kernel (128 / 256 pixels per MMA, 8- / 16-pixel-wide tiles; forcing also
-# sends small reflection-padded layers through the zero-padded TMA pass + border-ring pass)
-TMA_CONFIGS = {"auto": (1, 0, 0, 0), "gather": (0, 0, 0, 0), "tma-128px-tw8": (1, 1, 0, 3), "tma-256px-tw16": (1, 2, 0, 4)}
+# ScsfmConv.tune words (nnops.tune): the heuristic, the cp.async gather kernel alone (+ the cp.async weight-gradient
+# kernel), and two forced tilings of the persistent TMA kernel (128 / 256 pixels per MMA, 8- / 16-pixel-wide tiles;
+# forcing also sends small reflection-padded layers through the zero-padded TMA pass + border-ring pass), the second one
+# together with the TMA weight-gradient kernel
+TMA_CONFIGS = {"auto": dict(), "gather": dict(no_tma=1, wgrad=1), "tma-128px-tw8": dict(mt=1, tw_log2=3),
+               "tma-256px-tw16-wgradtma": dict(mt=2, tw_log2=4, wgrad=2)}
 
 
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("tma", sorted(TMA_CONFIGS))
 @pytest.mark.parametrize("case", TC_CASES)
-def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case, tma):
-    """TF32 tensor-core kernels: inputs rounded to 10-bit mantissas by the hardware, fp32 accumulation.
-    Operands are rounded to nearest TF32 in the loaders: expected relative L2 error ~3e-4; bound 1e-3."""
-    from scsfm import lib as L
+def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case, tma, mode):
+    """tcgen05 kernels.  "tf32": operands rounded to nearest TF32 by their producers, one product, fp32 accumulation:
+    expected relative L2 error ~3e-4, bound 1e-3.  "tf32x3": raw fp32 operands + their low parts, three products into the
+    same TMEM accumulator: fp32-level accuracy, bound 1e-5 (north_star: 1e-4)."""
     O = _ops()
-    if not hasattr(L.load(), "scsfm_conv2d_fwd_tc"):
-        pytest.skip("tensor-core kernels not built")
-    O.conv_tma_config(*TMA_CONFIGS[tma])
+    cx = O.ConvCtx(mode)
+    cx.tune = O.tune(**TMA_CONFIGS[tma])
+    x3 = mode == "tf32x3"
+    tol = 1e-5 if x3 else 1e-3
     B, H, W, Cin, Cout, k, stride, pad, pad_mode, act, bias = case
     g = torch.Generator().manual_seed(11)
     x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
@@ -329,57 +336,49 @@ def test_tcgen05_conv_fwd_and_dgrad_vs_fp64(case, tma):
     xc = x.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
     wc = w.detach().float().permute(0, 2, 3, 1).contiguous().to(DEV)
     bc = b.detach().float().to(DEV) if bias else None
-    # the tensor-core kernels expect operands already rounded to TF32 by their producers (SCSFM_ROUND_TF32)
-    for tns in (xc, wc):
-        O.round_tf32(tns, tns)
-    old = O.CONFIG["conv_mode"]
-    O.CONFIG["conv_mode"] = "tf32"
-    try:
-        assert O._use_tc("fwd", Cin, Cout, k, stride)
-        sums = torch.zeros(O.BN_SLOTS * Cout * 2, device=DEV, dtype=torch.float64)
-        yc = O.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1)
-        assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < 1e-3
-        s = sums.view(O.BN_SLOTS, Cout, 2).sum(0).cpu()
-        np.testing.assert_allclose(s[:, 0], yc.double().sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
-        np.testing.assert_allclose(s[:, 1], (yc.double() ** 2).sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
-        dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    w_lo = None
+    if x3:
+        w_lo = O.split_tf32(wc)
+    else:
+        # the single-product kernels expect operands already rounded to TF32 by their producers (SCSFM_ROUND_TF32)
+        for tns in (xc, wc):
+            O.round_tf32(tns, tns)
+    assert cx._use_tc("fwd", Cin, Cout, k, stride)
+    sums = torch.zeros(O.BN_SLOTS * Cout * 2, device=DEV, dtype=torch.float64)
+    yc = cx.conv_fwd(xc, wc, bc, stride, pad, pad_mode, act, sums, 1, w_lo)
+    assert rel_l2(yc.permute(0, 3, 1, 2), y.detach()) < tol
+    s = sums.view(O.BN_SLOTS, Cout, 2).sum(0).cpu()
+    np.testing.assert_allclose(s[:, 0], yc.double().sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(s[:, 1], (yc.double() ** 2).sum((0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
+    dc = dpre.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    if not x3:
         O.round_tf32(dc, dc)
-        if hasattr(L.load(), "scsfm_conv2d_wgrad_tc"):
-            assert O._use_tc("wgrad", Cin, Cout, k, stride)
-            dw = torch.zeros_like(wc)
-            db = torch.zeros(Cout, device=DEV) if bias else None
-            O.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
-            assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < 1e-3
-            if bias:
-                assert rel_l2(db, b.grad) < 1e-3     # dout was rounded to TF32 above
-        if stride in (1, 2):       # stride 2 runs as four parity-class sub-convolutions
-            assert O._use_tc("dgrad", Cin, Cout, k, stride)
-            O.invalidate_weight_cache()
-            if pad_mode == 0:
-                add = torch.randn(B, H, W, Cin, generator=g).to(DEV)
-                dx = O.conv_dgrad(dc, wc, xc.shape, stride, pad, add)
-                assert rel_l2((dx - add).permute(0, 3, 1, 2), x.grad) < 2e-3
-            else:
-                dpad = O.conv_dgrad(dc, wc, xc.shape, stride, pad, None, padded_input=True)
-                dx = torch.zeros_like(xc)
-                O.fold_plain(dpad, dx, None, O.ACT_NONE, accumulate=False)
-                assert rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 2e-3
-    finally:
-        O.CONFIG["conv_mode"] = old
-        O.invalidate_weight_cache()
-        O.conv_tma_config(1)
+    assert cx._use_tc("wgrad", Cin, Cout, k, stride)
+    dw = torch.zeros_like(wc)
+    db = torch.zeros(Cout, device=DEV) if bias else None
+    cx.conv_wgrad(xc, dc, dw, db, stride, pad, pad_mode)
+    assert rel_l2(dw.permute(0, 3, 1, 2), w.grad) < tol
+    if bias:
+        assert rel_l2(db, b.grad) < tol     # (tf32: dout was rounded to TF32 above)
+    assert cx._use_tc("dgrad", Cin, Cout, k, stride)       # stride 2 runs as four parity-class sub-convolutions
+    if pad_mode == 0:
+        add = torch.randn(B, H, W, Cin, generator=g).to(DEV)
+        dx = cx.conv_dgrad(dc, wc, xc.shape, stride, pad, add)
+        assert rel_l2((dx - add).permute(0, 3, 1, 2), x.grad) < 2 * tol
+    else:
+        dpad = cx.conv_dgrad(dc, wc, xc.shape, stride, pad, None, padded_input=True)
+        dx = torch.zeros_like(xc)
+        O.fold_plain(dpad, dx, None, O.ACT_NONE, accumulate=False)
+        assert rel_l2(dx.permute(0, 3, 1, 2), x.grad) < 2 * tol
 
 
 def test_disp_net_tf32_mode_vs_oracle(golden_nets):
-    """Whole DispResNet-18 forward/backward with the tensor-core kernels switched in (TF32, the arithmetic the
-    reference gets from cuDNN on a GPU by default): outputs within 1e-2, every parameter gradient within 5e-2 rel-L2
-    of the fp64 oracle."""
+    """Whole DispResNet-18 forward/backward with the single-product TF32 tensor-core kernels (the arithmetic the
+    reference gets from cuDNN on a GPU by default; NOT the parity mode, which is tf32x3 above): outputs within 1e-2, every
+    parameter gradient no worse than 3x stock PyTorch/cuDNN-TF32 against the fp64 oracle."""
     from oracle import nets as N
-    O = _ops()
-    old = O.CONFIG["conv_mode"]
-    O.CONFIG["conv_mode"] = "tf32"
-    try:
-        net = _build("disp", 18)
+    if True:
+        net = _build("disp", 18, "tf32")
         net.train()
         img1 = det_image("img1", 2, 64, 96)
         outs = net(img1.to(DEV))
@@ -408,24 +407,17 @@ def test_disp_net_tf32_mode_vs_oracle(golden_nets):
         print("tf32 mode: per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e | stock PyTorch/cuDNN TF32: median %.2e worst %.2e"
               % (med, errs[-1], med_stock, errs_stock[-1]))
         assert med < 3 * med_stock + 1e-3 and errs[-1] < 3 * errs_stock[-1] + 1e-2
-    finally:
-        O.CONFIG["conv_mode"] = old
-        O.invalidate_weight_cache()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
 def test_forward_multi_equals_separate_calls(mode):
     """Stacking the 3 DispResNet / 4 PoseResNet calls of a training step into one launch sequence must not change
     anything: per-call BatchNorm statistics, running-stat updates in call order, outputs, parameter gradients."""
-    import models
-    O = _ops()
-    old = O.CONFIG["conv_mode"]
-    O.CONFIG["conv_mode"] = mode
-    try:
+    if True:
         imgs = [det_image(n, 2, 64, 96).to(DEV) for n in ("img1", "img2", "img3")]
         tol = 1e-5 if mode == "fp32" else 2e-5     # identical kernels and inputs; only atomics order differs
         for kind in ("disp", "pose"):
-            a, b = _build(kind, 18), _build(kind, 18)
+            a, b = _build(kind, 18, mode), _build(kind, 18, mode)
             a.train(); b.train()
             if kind == "disp":
                 outs_a = [a(x) for x in imgs]
@@ -452,29 +444,23 @@ def test_forward_multi_equals_separate_calls(mode):
                     assert rel_l2(sb[k], sa[k]) < 1e-5, k
                 if "num_batches_tracked" in k:
                     assert int(sa[k]) == int(sb[k]) == (3 if kind == "disp" else 4)
-    finally:
-        O.CONFIG["conv_mode"] = old
-        O.invalidate_weight_cache()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
 @pytest.mark.parametrize("shape", [(6, 4, 6, 64, 3), (6, 8, 12, 64, 3), (8, 16, 24, 128, 4), (3, 5, 7, 32, 3)])
 def test_fused_batchnorm_sums_per_group(mode, shape):
     """Per-group BatchNorm partial sums out of the conv epilogue when several calls are stacked: groups whose
     row ranges straddle the 128-row (tensor-core) / 64-row (CUDA-core) tiles."""
     O = _ops()
     B, H, W, C, G = shape
-    old = O.CONFIG["conv_mode"]
-    O.CONFIG["conv_mode"] = mode
-    try:
+    cx = O.ConvCtx(mode)
+    if True:
         g = torch.Generator().manual_seed(5)
         x = torch.randn(B, H, W, C, generator=g).to(DEV)
         w = (torch.randn(C, 3, 3, C, generator=g) / (9 * C) ** 0.5).to(DEV)
         sums = torch.zeros(O.BN_SLOTS * G * C * 2, device=DEV, dtype=torch.float64)
-        y = O.conv_fwd(x, w, None, 1, 1, O.PAD_ZERO, O.ACT_NONE, sums, G)
+        y = cx.conv_fwd(x, w, None, 1, 1, O.PAD_ZERO, O.ACT_NONE, sums, G, O.split_tf32(w) if cx.split else None)
         got = sums.view(O.BN_SLOTS, G, C, 2).sum(0)
         yg = y.double().view(G, -1, C)
         np.testing.assert_allclose(got[..., 0].cpu(), yg.sum(1).cpu(), rtol=1e-5, atol=1e-4)
         np.testing.assert_allclose(got[..., 1].cpu(), (yg ** 2).sum(1).cpu(), rtol=1e-5, atol=1e-4)
-    finally:
-        O.CONFIG["conv_mode"] = old

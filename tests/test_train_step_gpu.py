@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def test_two_training_steps_match_the_oracle():
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_two_training_steps_match_the_oracle(mode):
+    """Both 1e-4 parity modes: exact CUDA-core convolutions and split-accumulate tcgen05 convolutions."""
     import models
     from oracle import nets as N
     from oracle import step as OS
@@ -27,7 +29,7 @@ def test_two_training_steps_match_the_oracle():
         b.load_state_dict(sd)
     disp, pose = disp.to(DEV).train(), pose.to(DEV).train()
     odisp.train(); opose.train()
-    tr = Trainer(disp, pose, lr=1e-4, with_auto_mask=0, distributed=False)
+    tr = Trainer(disp, pose, lr=1e-4, with_auto_mask=0, distributed=False, conv_mode=mode)
     opt = OS.make_optimizer(odisp, opose, lr=1e-4)
     c = lambda x: x.to(DEV)  # noqa: E731
     for it in range(2):
@@ -63,6 +65,64 @@ def test_two_training_steps_match_the_oracle():
     for k, v in disp.state_dict().items():
         if v.dtype == torch.float32 and "running" not in k:
             assert float((v.cpu() - osd[k]).abs().max()) <= 4.1e-4, k
+
+
+_FULL = {}
+
+
+def _full_size_oracle():
+    """One oracle step (fp32 and fp64) on the BENCHMARKED configuration: B=4, 256x832, 2 refs, ssim + mask + auto-mask
+    (BASELINE config 2).  Computed once per test session (CPU, ~1 minute)."""
+    if not _FULL:
+        from oracle import nets as N
+        from oracle import step as OS
+        from scsfm import synth
+        tgt, refs, K = synth.triplet(1234, 4, 256, 832)
+        out = {"inputs": (tgt, refs, K)}
+        for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            d, p = N.DispResNet(18).to(dt), N.PoseResNet(18).to(dt)
+            for net in (d, p):
+                net.load_state_dict({k: v.to(dt) for k, v in det_weights(net.state_dict()).items()})
+                net.train()
+            losses = OS.train_step(d, p, OS.make_optimizer(d, p, lr=1e-4), tgt.to(dt), [r.to(dt) for r in refs], K.to(dt),
+                                   num_scales=1, with_ssim=1, with_mask=1, with_auto_mask=1)
+            out[name] = ([float(v) for v in losses],
+                         {"disp." + k: q.grad.clone() for k, q in d.named_parameters() if q.grad is not None} |
+                         {"pose." + k: q.grad.clone() for k, q in p.named_parameters() if q.grad is not None})
+        _FULL.update(out)
+    return _FULL
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "fp32"])
+def test_full_size_benchmarked_step_vs_oracle(mode):
+    """The step bench.py times (B=4, 256x832, auto-mask on) against the oracle, in every convolution mode: the four
+    scalar losses and EVERY parameter gradient of both networks.  Yardstick for the gradients = the fp32 CPU oracle's own
+    error against the fp64 oracle (kink pixels and ReLU gates flip between any two evaluations).  tf32x3 and fp32 are the
+    parity modes (bound: 3x the fp32 oracle's own error); tf32 (single product, cuDNN's default arithmetic) is only
+    required to stay within 1e-2 on the losses and is reported."""
+    import models
+    from scsfm.trainer import Trainer
+    o = _full_size_oracle()
+    tgt, refs, K = o["inputs"]
+    disp, pose = models.DispResNet(18, False), models.PoseResNet(18, False)
+    for net in (disp, pose):
+        net.load_state_dict(det_weights(net.state_dict()))
+    tr = Trainer(disp.to(DEV).train(), pose.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False, conv_mode=mode)
+    got = [float(v) for v in tr.step(tgt.to(DEV), [r.to(DEV) for r in refs], K.to(DEV))]
+    grads = {"disp." + k: q.grad for k, q in disp.named_parameters()} | {"pose." + k: q.grad for k, q in pose.named_parameters()}
+    want64, g64 = o["f64"]
+    want32, g32 = o["f32"]
+    mine = sorted((rel_l2(grads[k], g64[k]), k) for k in g64)
+    ref = sorted(rel_l2(g32[k], g64[k]) for k in g64)
+    med, worst, rmed, rworst = mine[len(mine) // 2][0], mine[-1], ref[len(ref) // 2], ref[-1]
+    print("full-size step [%s]: losses %s (fp64 oracle %s) | parameter-gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s) | "
+          "fp32 CPU oracle's own: median %.2e worst %.2e" % (mode, [round(v, 6) for v in got], [round(v, 6) for v in want64], med,
+                                                            worst[0], worst[1], rmed, rworst))
+    if mode == "tf32":
+        np.testing.assert_allclose(got, want64, rtol=1e-2, atol=1e-5)
+        return
+    np.testing.assert_allclose(got, want64, rtol=1e-4, atol=1e-6)        # north_star: scalar losses within 1e-4
+    assert med < 3 * rmed + 1e-4 and worst[0] < 3 * rworst + 1e-3
 
 
 def test_step_issues_no_host_synchronisation():
@@ -113,10 +173,12 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert float((graphed.disp_net.flat_params() - eager.disp_net.flat_params()).abs().max()) <= 6.1e-4   # 3 steps x 2 lr
 
 
-def test_tf32_operand_mirror_and_batched_flips_stay_exact():
-    """tf32 mode shortcuts of the training loop: ArenaAdam writes the TF32-rounded operand copy of the parameters itself
-    (no rounding pass per network call) and all flipped data-gradient weights of a network are refreshed by ONE batched
-    launch.  Both must be bit-identical to the plain per-tensor kernels, eagerly and under CUDA-graph replay."""
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+def test_tf32_operand_mirror_and_batched_flips_stay_exact(mode):
+    """Tensor-core mode shortcuts of the training loop: ArenaAdam writes the operand mirror of the parameters itself (TF32-
+    rounded copy / low parts; no extra pass per network call) and all flipped data-gradient weights of a network are
+    refreshed by ONE batched launch.  Both must be bit-identical to the plain per-tensor kernels, eagerly and under
+    CUDA-graph replay."""
     import math
     import models
     from scsfm import nnops as O
@@ -128,17 +190,14 @@ def test_tf32_operand_mirror_and_batched_flips_stay_exact():
     def make():
         d, p = models.DispResNet(18, False), models.PoseResNet(18, False)
         d.load_state_dict(det_weights(d.state_dict())); p.load_state_dict(det_weights(p.state_dict()))
-        return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False)
+        return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False, conv_mode=mode)
 
     def mirror_in_sync(net):
         want = torch.empty_like(net._flat)
-        O.round_tf32(net._flat, want)
+        (O.split_tf32 if mode == "tf32x3" else O.round_tf32)(net._flat, want)
         return torch.equal(net._flat_tf32, want)
 
-    old = O.CONFIG["conv_mode"]
-    O.CONFIG["conv_mode"] = "tf32"
-    try:
-        O.invalidate_weight_cache()
+    if True:
         tr = make()
         for _ in range(3):                      # steps 2 and 3 run on the shortcuts
             losses = tr.step(*args)
@@ -148,24 +207,23 @@ def test_tf32_operand_mirror_and_batched_flips_stay_exact():
             assert net.trust_adam_mirror and net._tf32_version == net._versions()
             assert mirror_in_sync(net)
             net.refresh_operand_weights()       # batched flip refresh from the (current) mirror
-        cached = {k: v.clone() for k, v in O._flip_cache.items()}
-        assert len(cached) > 20
-        O.invalidate_weight_cache()
         seen = 0
         for net in nets:
-            lo = net._flat_tf32.data_ptr()
+            cached = {k: v[1].clone() for k, v in net.ctx._flips.items()}
+            assert len(cached) > 10
+            src = net._flat if mode == "tf32x3" else net._flat_tf32      # arena the flips are derived from
+            lo = src.data_ptr()
+            fresh = O.ConvCtx(mode)
             for key, got in cached.items():
-                ptr, shape, stride, pad = key
-                if not (lo <= ptr < lo + 4 * net._flat_tf32.numel()):
-                    continue
+                ptr, shape, stride, pad, operand = key
+                assert lo <= ptr < lo + 4 * src.numel()
                 off = (ptr - lo) // 4
-                w = net._flat_tf32[off:off + math.prod(shape)].view(shape)
+                w = src[off:off + math.prod(shape)].view(shape)
                 assert w.data_ptr() == ptr
-                assert torch.equal(O.flipped_weights(w, stride, pad), got), key
+                assert torch.equal(fresh.flipped_weights(w, stride, pad, operand), got), key
                 seen += 1
-        assert seen == len(cached)
+        assert seen > 40
         # the same loop as one CUDA graph per step
-        O.invalidate_weight_cache()
         gr = make()
         gr.capture(*args)
         for _ in range(2):
@@ -177,6 +235,3 @@ def test_tf32_operand_mirror_and_batched_flips_stay_exact():
         with torch.no_grad():
             next(iter(gr.disp_net.parameters())).mul_(1.5)
         assert gr.disp_net._tf32_version != gr.disp_net._versions()
-    finally:
-        O.CONFIG["conv_mode"] = old
-        O.invalidate_weight_cache()
