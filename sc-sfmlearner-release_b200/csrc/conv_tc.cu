@@ -173,6 +173,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         }
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
         constexpr int CW = BN < 32 ? BN : 32;
+        const int nacc = min(Cfg::NACC, KB * npass);            // accumulators that received at least one k-block
 #pragma unroll 1
         for (int cc = half; cc < BN / CW; cc += FW_PWARPS / 4) {
             uint32_t r[32];
@@ -180,6 +181,14 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
             if (CW == 32) tc::tmem_ld32(taddr, r);
             else tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
+            for (int a = 1; a < nacc; ++a) {                   // the round-robin partial accumulators, added in fp32 (RN)
+                uint32_t q[32];
+                if (CW == 32) tc::tmem_ld32(taddr + (uint32_t)(a * Cfg::ACC_COLS), q);
+                else tc::tmem_ld16(taddr + (uint32_t)(a * Cfg::ACC_COLS), q);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -261,7 +270,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                 for (int j = 0; j < TBK / 8; ++j) {
                     const uint64_t da = tc::make_smem_desc(a_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
                     const uint64_t db = tc::make_smem_desc(b_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
-                    tc::mma_tf32(tmem_base, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + (uint32_t)((kb % Cfg::NACC) * Cfg::ACC_COLS), da, db, idesc, (kb >= Cfg::NACC || j != 0) ? 1u : 0u);
                 }
                 tc::mma_commit(bar_empty + s);           // frees the stage once these MMAs have read it
             }
@@ -307,7 +316,9 @@ struct WgCfg {
     static constexpr int STAGES = 3;
     static constexpr int A_BYTES = 32 * TBM * 4;        // 32 pixels x 128 (tap,c)
     static constexpr int B_BYTES = 32 * BN * 4;         // 32 pixels x BN output channels
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int NACC = BN >= 128 ? 1 : (BN >= 64 ? 2 : 4);      // round-robin accumulators (see TcCfg); 3 CTAs per SM fit
+    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;   // 128
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
@@ -449,11 +460,20 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         tc::fence_after_thread_sync();
         const int quarter = warp & 3, half = warp >> 2;
         const int row = m0 + quarter * 32 + lane;
+        const int nacc = min(Cfg::NACC, KB * npass);
 #pragma unroll 1
         for (int cc = half; cc < BN / 32; cc += FW_PWARPS / 4) {
             uint32_t r[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32);
+            tc::tmem_ld32(taddr, r);
             tc::tmem_ld_wait();
+            for (int a = 1; a < nacc; ++a) {                   // round-robin partial accumulators, added in fp32 (RN)
+                uint32_t q[32];
+                tc::tmem_ld32(taddr + (uint32_t)(a * Cfg::ACC_COLS), q);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+            }
             if (row < Mtot) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -479,7 +499,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
                     // LBO = 512 B between 32-channel atoms, SBO = distance between 4-pixel groups; 2 groups per MMA
                     const uint64_t da = tc::make_smem_desc(a_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
                     const uint64_t db = tc::make_smem_desc(b_addr + j * (2 * (BN / 32) * 512), 512, (BN / 32) * 512, tc::LAYOUT_SW128_BASE32B);
-                    tc::mma_tf32(tmem_base, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + (uint32_t)((kb % Cfg::NACC) * Cfg::ACC_COLS), da, db, idesc, (kb >= Cfg::NACC || j != 0) ? 1u : 0u);
                 }
                 tc::mma_commit(bar_empty + s);
             }
@@ -522,6 +542,14 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
+    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
+    if (npass > 1) {
+        // split-accumulate (parity) mode: bound every accumulation chain to ~160 tcgen05.mma (truncation bias ~5e-6):
+        // chain = k-blocks * 4 MMAs * passes / NACC.  More, shorter CTAs; their partial tiles are added with fp32 atomics (RN)
+        const int kb_max = 160 * Cfg::NACC / (4 * npass);
+        const int need = (npix + 32 * kb_max - 1) / (32 * kb_max);
+        if (splits < need) splits = need;
+    }
     const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
     dim3 grid(mt, nt, (npix + pps - 1) / pps);
     conv_wgrad_tc_kernel<BN, BORDER><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
@@ -775,7 +803,14 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     int rc;
     ScsfmConv zp = *p;                         // the same layer with zero padding (what the TMA kernel computes)
     zp.pad_mode = SCSFM_PADMODE_ZERO;
-    const int kernel = (int)((p->tune >> 12) & 3u);       // SCSFM_TUNE_WGRAD: 0 auto, 1 cp.async kernel, 2 TMA kernel
+    int kernel = (int)((p->tune >> 12) & 3u);       // SCSFM_TUNE_WGRAD: 0 auto, 1 cp.async kernel, 2 TMA kernel
+    if (kernel == 0) {
+        // split-accumulate (parity) mode: the TMA kernel drains its accumulation chains into registers, so it needs no extra
+        // split-K to bound the truncation bias; the cp.async kernel does (cheap only when dW is small, i.e. thin layers).
+        // Plain TF32: the cp.async kernel is as fast or faster everywhere (profiles/r02_wgrad_tma_check.txt).
+        const bool split = p->in_lo != nullptr || p->dout_lo != nullptr;
+        kernel = (split && p->Cout >= 64) ? 2 : 1;
+    }
     if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
     } else if (kernel == 2 && p->pad_mode == PADMODE_REFLECT && p->pad == 1 && p->Ho >= 3 && p->Wo >= 3 &&

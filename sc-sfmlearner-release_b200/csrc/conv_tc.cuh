@@ -15,11 +15,17 @@ constexpr int FW_PWARPS = 8;          // forward/dgrad kernel: 8 producer/epilog
 constexpr int FW_THREADS = (FW_PWARPS + 1) * 32;
 constexpr int A_STAGE_BYTES = TBM * 128;
 
+// The tensor core adds into a TMEM accumulator with truncation: a chain of n tcgen05.mma carries a systematic relative error
+// of ~3e-8 * n (measured; 1e-4 after a few thousand).  The kernels whose epilogue warps are busy producing (cp.async gather
+// kernels) therefore spread consecutive k-blocks round-robin over NACC accumulators (chains NACC times shorter) and add them
+// up in registers (round-to-nearest) in the epilogue.
 template <int BN>
 struct TcCfg {
     static constexpr int STAGES = 3;
     static constexpr int B_STAGE_BYTES = BN * 128;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int NACC = BN >= 128 ? 2 : 4;
+    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;      // column stride between accumulators
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;       // 64 .. 256: two CTAs per SM still fit in the 512 columns
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 };
 

@@ -52,6 +52,10 @@ struct TmaGeom {
     // split-accumulate passes per (channel chunk, dx): pass i multiplies (activations: lo if a_lo bit i else raw) by
     // (weights: lo if w_lo bit i else raw); plain TF32 = one pass with both masks 0
     int npass, a_lo, w_lo;
+    // accumulation chunks: the tensor core adds into the TMEM accumulator with truncation (measured: relative error ~ 3e-8 per
+    // tcgen05.mma of the chain, a systematic bias), so a chain is cut after `cpg` channel chunks (~100 MMAs) and the epilogue
+    // warps add the partial accumulators in registers (round-to-nearest).  cpg >= chunks: one chain per tile (plain TF32 mode).
+    int cpg;
     unsigned long long* dbg; // optional per-CTA cycle counters (ScsfmConv.debug), 8 per CTA; NULL = off
 };
 
@@ -159,14 +163,19 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             int j = 0;
             long long t_full = 0, t_acc = 0;
             const long long t_begin = tma_clock();
+            int jc = 0;                                    // accumulation chunks issued so far: TMEM buffer jc & 1
             for (int w = blockIdx.x; w < g.num_work; w += gridDim.x, ++j) {
-                const int buf = j & 1;
-                const long long ta = g.dbg ? tma_clock() : 0;
-                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // epilogue of tile j-2 has drained this buffer
-                if (g.dbg) t_acc += tma_clock() - ta;
-                tc::fence_after_thread_sync();
-                const uint32_t acc = tmem_base + (uint32_t)(buf * NPIX);
+                uint32_t acc = 0;
                 for (int ck = 0; ck < chunks; ++ck) {
+                    const bool first_of_chain = ck % g.cpg == 0;
+                    if (first_of_chain) {
+                        const int buf = jc & 1;
+                        const long long ta = g.dbg ? tma_clock() : 0;
+                        tc::mbar_wait(acc_empty + buf, ((jc >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
+                        if (g.dbg) t_acc += tma_clock() - ta;
+                        tc::fence_after_thread_sync();
+                        acc = tmem_base + (uint32_t)(buf * NPIX);
+                    }
                     const int rem = p.Cin - ck * TBK;
                     const int k8 = rem >= TBK ? TBK / 8 : (rem + 7) / 8;           // K8 slices holding real channels
                     for (int dx = 0; dx < v.kw; ++dx) {
@@ -181,7 +190,7 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                                 uint64_t dw = desc0 + (uint64_t)((w_addr + (uint32_t)(dy * W_TILE)) >> 4);      // M side: weights
                                 uint64_t dx_ = desc0 + (uint64_t)((x_addr + (uint32_t)dy * dy_bytes) >> 4);    // N side: pixels
                                 for (int q = 0; q < k8; ++q) {
-                                    tc::mma_tf32(acc, dw, dx_, idesc, (ck | dx | ps | dy | q) != 0 ? 1u : 0u);
+                                    tc::mma_tf32(acc, dw, dx_, idesc, (!first_of_chain || (dx | ps | dy | q) != 0) ? 1u : 0u);
                                     dw += 2;                     // next K8 slice: +32 bytes inside the 128-byte swizzle row
                                     dx_ += 2;
                                 }
@@ -190,8 +199,11 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                             if (++s == g.stages) { s = 0; ph ^= 1; }
                         }
                     }
+                    if ((ck + 1) % g.cpg == 0 || ck == chunks - 1) {      // end of a chain: hand the buffer to the epilogue warps
+                        tc::mma_commit(acc_full + (jc & 1));
+                        ++jc;
+                    }
                 }
-                tc::mma_commit(acc_full + buf);
             }
             if (g.dbg) {
                 g.dbg[blockIdx.x * 8 + 2] = (unsigned long long)t_full;
@@ -222,7 +234,10 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
         const long long img_step = (long long)v.out_H * v.out_W * N;       // elements between images
         const int row_step = v.out_sy * v.out_W * N;                        // ... between tile rows
         const int px_step = v.out_sx * N;                                   // ... between tile columns
-        int j = 0;
+        constexpr int RPT = NPIX / 64;               // 32-column groups of the accumulator this warp owns: (2 * rd + half) * 32
+        const int nchains = (chunks + g.cpg - 1) / g.cpg;
+        float accr[RPT][32];                         // the tile's sums (this thread's TMEM lane = channel, RPT * 32 pixels)
+        int j = 0, jc = 0;
         long long t_wait = 0, t_ld = 0;
         const long long t_begin = tma_clock();
         for (int w = blockIdx.x; w < g.num_work; w += gridDim.x, ++j) {
@@ -232,39 +247,61 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             const int ty = t % g.tiles_y;
             const int b = t / g.tiles_y;
             const int y0 = ty * (MT * TH), x0 = tx * TW;
-            const int buf = j & 1;
-            const long long t0 = g.dbg ? tma_clock() : 0;
-            tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
-            if (g.dbg) t_wait += tma_clock() - t0;
-            tc::fence_after_thread_sync();
             const int cv = min(TBM, N - n0);                     // real channels of this Cout tile (multiple of 4)
             const bool loader = quarter * 32 < cv;                // warp-uniform: this lane quarter holds real channels
+            // ---- drain the tile's accumulation chains into registers (TMEM -> registers, fp32 round-to-nearest adds)
+            for (int c = 0; c < nchains; ++c, ++jc) {
+                const int buf = jc & 1;
+                const long long t0 = g.dbg ? tma_clock() : 0;
+                tc::mbar_wait(acc_full + buf, (jc >> 1) & 1);
+                if (g.dbg) t_wait += tma_clock() - t0;
+                tc::fence_after_thread_sync();
+                if (loader) {
+                    const uint32_t src = tmem_base + (uint32_t)(buf * NPIX) + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
+                    const long long tl0 = g.dbg ? tma_clock() : 0;
+                    if (c == 0) {
+#pragma unroll
+                        for (int rd = 0; rd < RPT; ++rd) {
+                            uint32_t r[32];
+                            tc::tmem_ld32(src + (uint32_t)(rd * 64), r);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) accr[rd][i] = __uint_as_float(r[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int rd = 0; rd < RPT; ++rd) {
+                            uint32_t r[32];
+                            tc::tmem_ld32(src + (uint32_t)(rd * 64), r);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) accr[rd][i] += __uint_as_float(r[i]);
+                        }
+                    }
+                    if (g.dbg) t_ld += tma_clock() - tl0;
+                }
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acc_empty + buf);      // this warp's tcgen05.ld of the buffer are done
+            }
             const bool ch_ok = 4 * c4 < cv;
             const int n = n0 + 4 * c4;                            // first of this thread's 4 channels
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias != nullptr && ch_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            const uint32_t acc = tmem_base + (uint32_t)(buf * NPIX) + ((uint32_t)(quarter * 32) << 16);
             const long long tile_off = (long long)b * img_step + (long long)(y0 * v.out_sy + v.out_oy) * (v.out_W * N) +
                                        (long long)(x0 * v.out_sx + v.out_ox) * N + n;
             float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int rd = 0; rd < NPIX / 64; ++rd) {
+#pragma unroll
+            for (int rd = 0; rd < RPT; ++rd) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // A: everybody has finished reading the previous round
                 if (loader) {
-                    uint32_t r[32];
-                    const long long tl0 = g.dbg ? tma_clock() : 0;
-                    tc::tmem_ld32(acc + (uint32_t)((2 * rd + half) * 32), r);
-                    tc::tmem_ld_wait();
-                    if (g.dbg) t_ld += tma_clock() - tl0;
                     float* dst = T + (32 * half) * TS + quarter * 32 + lane;
                     if (quarter * 32 + lane < CT) {            // (a 16-channel tile only has 16 real lanes)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) dst[i * TS] = __uint_as_float(r[i]);     // consecutive lanes = consecutive words
+                        for (int i = 0; i < 32; ++i) dst[i * TS] = accr[rd][i];     // consecutive lanes = consecutive words
                     }
                 }
-                if (rd == NPIX / 64 - 1) tc::fence_before_thread_sync();
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // B: the round's 64 x cv values are in T
-                if (rd == NPIX / 64 - 1 && lane == 0) tc::mbar_arrive(acc_empty + buf);      // every tcgen05.ld of the tile is done
 #pragma unroll
                 for (int k = 0; k < ITER; ++k) {
                     const int px = px0 + k * PXSTEP;
@@ -375,6 +412,13 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
     g.npass = 1; g.a_lo = 0; g.w_lo = 0;
     if (p.in_lo != nullptr) { g.a_lo |= 1 << g.npass; ++g.npass; }
     if (p.w_lo != nullptr) { g.w_lo |= 1 << g.npass; ++g.npass; }
+    {
+        const int chunks = (p.Cin + TBK - 1) / TBK;
+        const int mma_per_chunk = v.kw * g.npass * v.kh * (TBK / 8);
+        // split mode: chains of ~100 MMAs (bias ~3e-6); plain TF32 (operand rounding 3e-4 dominates): one chain per tile
+        g.cpg = g.npass > 1 ? (96 + mma_per_chunk - 1) / mma_per_chunk : chunks;
+        if (g.cpg < 1) g.cpg = 1;
+    }
     const size_t smem = (size_t)fixed + (size_t)g.stages * g.stage_bytes;
     CUtensorMap amap, wmap, amap_lo, wmap_lo;
     for (int lo = 0; lo < 2; ++lo) {

@@ -36,6 +36,9 @@ struct WtGeom {
     int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4)
     int stages, patch_bytes, stage_bytes;
     int npass, x_lo, d_lo;       // split-accumulate passes per tile: pass i uses lo(input) if x_lo bit i, lo(dout) if d_lo bit i
+    int tpc;                     // pixel tiles per accumulation chain: the tensor core adds into TMEM with truncation (bias ~3e-8 per
+                                 // MMA of a chain), so the epilogue warps drain the accumulator into registers (round-to-nearest adds)
+                                 // every tpc tiles while the MMAs continue in the second TMEM buffer
 };
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
@@ -45,8 +48,9 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* bar_empty = bar_full + WT_MAX_STAGES;
-    uint64_t* bar_acc = bar_empty + WT_MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
+    uint64_t* acc_full = bar_empty + WT_MAX_STAGES;      // [2] tcgen05.commit at the end of a chain
+    uint64_t* acc_empty = acc_full + 2;                  // [2] one arrival per epilogue warp once the buffer is drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint8_t* ring = smem + 1024;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,10 +69,13 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             tc::mbar_init(bar_full + s, 1);
             tc::mbar_init(bar_empty + s, 1);
         }
-        tc::mbar_init(bar_acc, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(acc_full + i, 1);
+            tc::mbar_init(acc_empty + i, WT_EWARPS);
+        }
         tc::fence_barrier_init();
     }
-    if (warp == WT_EWARPS + 1) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == WT_EWARPS + 1) tc::tmem_alloc(tmem_slot, 512);       // two accumulator buffers of 256 columns
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
@@ -121,47 +128,87 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             const int slices = TW >> 3;                       // 8-pixel slices per tile row
             int s = 0;
             uint32_t ph = 0;
-            for (int it = 0; it < ntiles * g.npass; ++it) {
-                tc::mbar_wait(bar_full + s, ph);
-                tc::fence_after_thread_sync();
-                const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
-                const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
-                for (int r = 0; r < TH; ++r) {
-                    for (int kq = 0; kq < slices; ++kq) {
-                        const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
-                        const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
-                        tc::mma_tf32(tmem_base, dm, dn, idesc, (it != 0 || r != 0 || kq != 0) ? 1u : 0u);
-                    }
+            int jc = 0;                                      // chains issued: TMEM buffer jc & 1
+            for (int t = 0; t < ntiles; ++t) {
+                const bool first_tile = t % g.tpc == 0;
+                const uint32_t acc = tmem_base + (uint32_t)((jc & 1) * 256);
+                if (first_tile) {
+                    tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
+                    tc::fence_after_thread_sync();
                 }
-                tc::mma_commit(bar_empty + s);
-                if (++s == g.stages) { s = 0; ph ^= 1; }
+                for (int ps = 0; ps < g.npass; ++ps) {
+                    tc::mbar_wait(bar_full + s, ph);
+                    tc::fence_after_thread_sync();
+                    const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
+                    const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
+                    for (int r = 0; r < TH; ++r) {
+                        for (int kq = 0; kq < slices; ++kq) {
+                            const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
+                            const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
+                            tc::mma_tf32(acc, dm, dn, idesc, (!first_tile || ps != 0 || r != 0 || kq != 0) ? 1u : 0u);
+                        }
+                    }
+                    tc::mma_commit(bar_empty + s);
+                    if (++s == g.stages) { s = 0; ph ^= 1; }
+                }
+                if ((t + 1) % g.tpc == 0 || t == ntiles - 1) {
+                    tc::mma_commit(acc_full + (jc & 1));
+                    ++jc;
+                }
             }
-            tc::mma_commit(bar_acc);
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue: dw[o][(dy, dx, channel)] += D[o][...]
-        tc::mbar_wait(bar_acc, 0);
-        tc::fence_after_thread_sync();
         const int quarter = warp & 3, half = warp >> 2;
         const int o = n0 + quarter * 32 + lane;
         const int Mtot = p.kh * p.kw * p.Cin;
-        if (n0 + quarter * 32 < p.Cout) {                 // warp-uniform: this lane quarter holds real output channels
-#pragma unroll 1
-            for (int a = half; a < natoms; a += WT_EWARPS / 4) {
+        const bool real = n0 + quarter * 32 < p.Cout;     // warp-uniform: this lane quarter holds real output channels
+        constexpr int APW = 3;                            // accumulator atoms (32 columns) per warp: a = half + 2 * ai < kh * G <= 6
+        float accr[APW][32];
+        const int nchains = (ntiles + g.tpc - 1) / g.tpc;
+        for (int c = 0; c < nchains; ++c) {
+            const int buf = c & 1;
+            tc::mbar_wait(acc_full + buf, (c >> 1) & 1);
+            tc::fence_after_thread_sync();
+            if (real) {
+                const uint32_t src = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+                for (int ai = 0; ai < APW; ++ai) {
+                    const int a = half + 2 * ai;
+                    if (a < natoms) {
+                        uint32_t r[32];
+                        tc::tmem_ld32(src + (uint32_t)(a * 32), r);
+                        tc::tmem_ld_wait();
+                        if (c == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) accr[ai][i] = __uint_as_float(r[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) accr[ai][i] += __uint_as_float(r[i]);
+                        }
+                    }
+                }
+            }
+            tc::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+        }
+        if (real) {
+#pragma unroll
+            for (int ai = 0; ai < APW; ++ai) {
+                const int a = half + 2 * ai;
+                if (a >= natoms) continue;
                 const int dy = a / g.G, c = a - dy * g.G;
                 const int ch0 = 32 * (chunk0 + c);            // first input channel of this atom
                 if (ch0 >= p.Cin) continue;                   // padding chunk of the last group
-                uint32_t r[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 32), r);
-                tc::tmem_ld_wait();
                 if (o < p.Cout) {
                     float* dst = p.dw + (size_t)o * Mtot + (size_t)(dy * p.kw + dx) * p.Cin + ch0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         if (ch0 + j < p.Cin)                  // Cin % 4 == 0: a vector never straddles the end
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
-                                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(accr[ai][j]), "f"(accr[ai][j + 1]),
+                                         "f"(accr[ai][j + 2]), "f"(accr[ai][j + 3])
                                          : "memory");
                 }
             }
@@ -169,7 +216,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     }
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == WT_EWARPS + 1) tc::tmem_dealloc(tmem_base, 256);
+    if (warp == WT_EWARPS + 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 bool conv_wgrad_tma_eligible(const ScsfmConv& p) {
@@ -213,6 +260,8 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     g.npass = 1; g.x_lo = 0; g.d_lo = 0;
     if (p.in_lo != nullptr) { g.x_lo |= 1 << g.npass; ++g.npass; }
     if (p.dout_lo != nullptr) { g.d_lo |= 1 << g.npass; ++g.npass; }
+    // split mode: chains of <= 96 MMAs (16 per tile and pass); plain TF32: one chain per CTA
+    g.tpc = g.npass > 1 ? (96 / (16 * g.npass) > 0 ? 96 / (16 * g.npass) : 1) : g.tiles_per_split;
     CUtensorMap xmap, dmap, xmap_lo, dmap_lo;
     for (int lo = 0; lo < 2; ++lo) {
         const float* base = lo ? p.in_lo : p.in;

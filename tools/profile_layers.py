@@ -1,5 +1,5 @@
 """Per-launch CUDA-event profile of one training step: every conv call with its shape, time, TFLOP/s.
-Usage: python tools/profile_layers.py [fp32|tf32]"""
+Usage: python tools/profile_layers.py [fp32|tf32|tf32x3] [kitti_r18|kitti_r50|nyu_r18]"""
 import collections
 import os
 import sys
@@ -9,16 +9,18 @@ sys.path.insert(0, os.path.join(ROOT, "sc-sfmlearner-release_b200"))
 import torch  # noqa: E402
 
 import models  # noqa: E402
-from scsfm import lib as L, nnops, synth  # noqa: E402
+from scsfm import lib as L, synth  # noqa: E402
 from scsfm.trainer import Trainer  # noqa: E402
 
 
 def main():
-    nnops.CONFIG["conv_mode"] = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+    dl, pl, H, W, n_ref, B, kind = {"kitti_r18": (18, 18, 256, 832, 2, 4, "kitti"), "kitti_r50": (50, 50, 256, 832, 2, 2, "kitti"),
+                                    "nyu_r18": (18, 18, 256, 320, 1, 8, "nyu")}[sys.argv[2] if len(sys.argv) > 2 else "kitti_r18"]
     dev = "cuda"
-    tr = Trainer(models.DispResNet(18, False).to(dev).train(), models.PoseResNet(18, False).to(dev).train(),
-                 with_auto_mask=1, distributed=False)
-    tgt, refs, K = synth.triplet(0, 4, 256, 832)
+    tr = Trainer(models.DispResNet(dl, False).to(dev).train(), models.PoseResNet(pl, False).to(dev).train(),
+                 with_auto_mask=1, distributed=False, conv_mode=mode)
+    tgt, refs, K = synth.triplet(0, B, H, W, n_ref, kind)
     args = (tgt.to(dev), [r.to(dev) for r in refs], K.to(dev))
     for _ in range(2):
         tr.step(*args)
@@ -33,7 +35,12 @@ def main():
         a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += work
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
     total = sum(v[1] for v in agg.values())
-    print("total profiled %.2f ms" % total)
+    fams = collections.OrderedDict()
+    for (fam, _), (n, ms, _) in rows:
+        f = fams.setdefault(fam, [0, 0.0])
+        f[0] += n; f[1] += ms
+    print("total profiled %.2f ms  [%s]" % (total, mode))
+    print("  ".join("%s %.2f" % (k, v[1]) for k, v in sorted(fams.items(), key=lambda kv: -kv[1][1])))
     for (fam, tag), (n, ms, work) in rows[:70]:
         rate = work / (ms * 1e-3) / 1e12 if fam.startswith("conv") else work / (ms * 1e-3) / 1e9
         unit = "TF/s" if fam.startswith("conv") else "GB/s"
