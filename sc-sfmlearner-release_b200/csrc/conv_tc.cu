@@ -99,7 +99,8 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         int aoff[ROWS];
         uint32_t okm = 0;
         int it = 0;                                  // k-block counter across the passes: stage = it % STAGES
-        for (int ps = 0; ps < npass; ++ps) {
+        for (int q = 0; q < npass; ++q) {
+        const int ps = (q + 1) % npass;              // low-part passes first (added while the accumulators are small), raw x raw last
         const float* a_base = (ps == 1 && p.in_lo != nullptr) ? p.in_lo : p.in;
         const CUtensorMap* wm = (ps == npass - 1 && ps > 0 && p.w_lo != nullptr) ? &wmap_lo : &wmap;
         kc = 4 * c;
@@ -394,7 +395,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
         int pb, pho, pwo;
         int it = 0;                                  // k-block counter across the passes: stage = it % STAGES
-        for (int ps = 0; ps < npass; ++ps) {
+        for (int q = 0; q < npass; ++q) {
+        const int ps = (q + 1) % npass;              // low-part passes first (added while the accumulators are small), raw x raw last
         const float* a_base = (ps == 1 && p.in_lo != nullptr) ? p.in_lo : p.in;
         const float* b_base = (ps == npass - 1 && ps > 0 && p.dout_lo != nullptr) ? p.dout_lo : p.dout;
         {

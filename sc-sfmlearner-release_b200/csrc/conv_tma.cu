@@ -126,11 +126,16 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                 const int ty = t % g.tiles_y;
                 const int b = t / g.tiles_y;
                 const int y0 = ty * (MT * TH) + v.oy0, x0 = tx * TW + v.ox0;
-                for (int ck = 0; ck < chunks; ++ck) {
-                    for (int dx = 0; dx < v.kw; ++dx) {
-                        for (int ps = 0; ps < g.npass; ++ps) {
-                            const CUtensorMap* am = ((g.a_lo >> ps) & 1) ? &amap_lo : &amap;
-                            const CUtensorMap* wm = ((g.w_lo >> ps) & 1) ? &wmap_lo : &wmap;
+                // one accumulation chain = cpg channel chunks; inside a chain the low-part passes run FIRST (their sums are
+                // 2^-11 of the main term: added while the accumulator is still small they lose nothing to its truncation),
+                // the raw x raw pass last
+                for (int ck0 = 0; ck0 < chunks; ck0 += g.cpg)
+                for (int q = 0; q < g.npass; ++q) {
+                    const int ps = (q + 1) % g.npass;
+                    const CUtensorMap* am = ((g.a_lo >> ps) & 1) ? &amap_lo : &amap;
+                    const CUtensorMap* wm = ((g.w_lo >> ps) & 1) ? &wmap_lo : &wmap;
+                    for (int ck = ck0; ck < min(chunks, ck0 + g.cpg); ++ck) {
+                        for (int dx = 0; dx < v.kw; ++dx) {
                             const long long t0 = g.dbg ? tma_clock() : 0;
                             tc::mbar_wait(bar_empty + s, ph ^ 1);
                             if (g.dbg) t_wait += tma_clock() - t0;
@@ -165,21 +170,19 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             const long long t_begin = tma_clock();
             int jc = 0;                                    // accumulation chunks issued so far: TMEM buffer jc & 1
             for (int w = blockIdx.x; w < g.num_work; w += gridDim.x, ++j) {
-                uint32_t acc = 0;
-                for (int ck = 0; ck < chunks; ++ck) {
-                    const bool first_of_chain = ck % g.cpg == 0;
-                    if (first_of_chain) {
-                        const int buf = jc & 1;
-                        const long long ta = g.dbg ? tma_clock() : 0;
-                        tc::mbar_wait(acc_empty + buf, ((jc >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
-                        if (g.dbg) t_acc += tma_clock() - ta;
-                        tc::fence_after_thread_sync();
-                        acc = tmem_base + (uint32_t)(buf * NPIX);
-                    }
+                for (int ck0 = 0; ck0 < chunks; ck0 += g.cpg) {          // one accumulation chain (same loop nest as the producer)
+                    const int buf = jc & 1;
+                    const long long ta = g.dbg ? tma_clock() : 0;
+                    tc::mbar_wait(acc_empty + buf, ((jc >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
+                    if (g.dbg) t_acc += tma_clock() - ta;
+                    tc::fence_after_thread_sync();
+                    const uint32_t acc = tmem_base + (uint32_t)(buf * NPIX);
+                for (int q = 0; q < g.npass; ++q) {
+                    for (int ck = ck0; ck < min(chunks, ck0 + g.cpg); ++ck) {
+                    const bool first_of_chain = q == 0 && ck == ck0;
                     const int rem = p.Cin - ck * TBK;
                     const int k8 = rem >= TBK ? TBK / 8 : (rem + 7) / 8;           // K8 slices holding real channels
-                    for (int dx = 0; dx < v.kw; ++dx) {
-                        for (int ps = 0; ps < g.npass; ++ps) {
+                        for (int dx = 0; dx < v.kw; ++dx) {
                             const long long t0 = g.dbg ? tma_clock() : 0;
                             tc::mbar_wait(bar_full + s, ph);
                             if (g.dbg) t_full += tma_clock() - t0;
@@ -189,8 +192,8 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                             for (int dy = 0; dy < v.kh; ++dy) {
                                 uint64_t dw = desc0 + (uint64_t)((w_addr + (uint32_t)(dy * W_TILE)) >> 4);      // M side: weights
                                 uint64_t dx_ = desc0 + (uint64_t)((x_addr + (uint32_t)dy * dy_bytes) >> 4);    // N side: pixels
-                                for (int q = 0; q < k8; ++q) {
-                                    tc::mma_tf32(acc, dw, dx_, idesc, (!first_of_chain || (dx | ps | dy | q) != 0) ? 1u : 0u);
+                                for (int q8 = 0; q8 < k8; ++q8) {
+                                    tc::mma_tf32(acc, dw, dx_, idesc, (!first_of_chain || (dx | dy | q8) != 0) ? 1u : 0u);
                                     dw += 2;                     // next K8 slice: +32 bytes inside the 128-byte swizzle row
                                     dx_ += 2;
                                 }
@@ -199,10 +202,9 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                             if (++s == g.stages) { s = 0; ph ^= 1; }
                         }
                     }
-                    if ((ck + 1) % g.cpg == 0 || ck == chunks - 1) {      // end of a chain: hand the buffer to the epilogue warps
-                        tc::mma_commit(acc_full + (jc & 1));
-                        ++jc;
-                    }
+                }
+                    tc::mma_commit(acc_full + buf);          // end of the chain: hand the buffer to the epilogue warps
+                    ++jc;
                 }
             }
             if (g.dbg) {

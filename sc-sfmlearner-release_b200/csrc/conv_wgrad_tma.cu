@@ -92,15 +92,18 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             const uint32_t tx_bytes = (uint32_t)(g.atoms_m * TBM * 128) + (uint32_t)(prows * g.G) * row_bytes;
             int s = 0;
             uint32_t ph = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                int q = t;
-                const int tx = q % g.tiles_x; q /= g.tiles_x;
-                const int ty = q % g.tiles_y;
-                const int b = q / g.tiles_y;
-                const int y0 = ty * TH, x0 = tx * TW;
-                for (int ps = 0; ps < g.npass; ++ps) {
-                    const CUtensorMap* xm = ((g.x_lo >> ps) & 1) ? &xmap_lo : &xmap;
-                    const CUtensorMap* dm = ((g.d_lo >> ps) & 1) ? &dmap_lo : &dmap;
+            // one accumulation chain = tpc tiles; inside a chain the low-part passes run first, the raw x raw pass last
+            for (int tc0 = t_begin; tc0 < t_end; tc0 += g.tpc)
+            for (int qp = 0; qp < g.npass; ++qp) {
+                const int ps = (qp + 1) % g.npass;
+                const CUtensorMap* xm = ((g.x_lo >> ps) & 1) ? &xmap_lo : &xmap;
+                const CUtensorMap* dm = ((g.d_lo >> ps) & 1) ? &dmap_lo : &dmap;
+                for (int t = tc0; t < min(t_end, tc0 + g.tpc); ++t) {
+                    int q = t;
+                    const int tx = q % g.tiles_x; q /= g.tiles_x;
+                    const int ty = q % g.tiles_y;
+                    const int b = q / g.tiles_y;
+                    const int y0 = ty * TH, x0 = tx * TW;
                     tc::mbar_wait(bar_empty + s, ph ^ 1);
                     const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
                     tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
@@ -129,32 +132,28 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             int s = 0;
             uint32_t ph = 0;
             int jc = 0;                                      // chains issued: TMEM buffer jc & 1
-            for (int t = 0; t < ntiles; ++t) {
-                const bool first_tile = t % g.tpc == 0;
+            for (int tc0 = 0; tc0 < ntiles; tc0 += g.tpc, ++jc) {
                 const uint32_t acc = tmem_base + (uint32_t)((jc & 1) * 256);
-                if (first_tile) {
-                    tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
-                    tc::fence_after_thread_sync();
-                }
-                for (int ps = 0; ps < g.npass; ++ps) {
-                    tc::mbar_wait(bar_full + s, ph);
-                    tc::fence_after_thread_sync();
-                    const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
-                    const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
-                    for (int r = 0; r < TH; ++r) {
-                        for (int kq = 0; kq < slices; ++kq) {
-                            const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
-                            const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
-                            tc::mma_tf32(acc, dm, dn, idesc, (!first_tile || ps != 0 || r != 0 || kq != 0) ? 1u : 0u);
+                tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
+                tc::fence_after_thread_sync();
+                for (int qp = 0; qp < g.npass; ++qp) {
+                    for (int t = tc0; t < min(ntiles, tc0 + g.tpc); ++t) {
+                        tc::mbar_wait(bar_full + s, ph);
+                        tc::fence_after_thread_sync();
+                        const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
+                        const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
+                        for (int r = 0; r < TH; ++r) {
+                            for (int kq = 0; kq < slices; ++kq) {
+                                const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
+                                const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
+                                tc::mma_tf32(acc, dm, dn, idesc, (qp != 0 || t != tc0 || r != 0 || kq != 0) ? 1u : 0u);
+                            }
                         }
+                        tc::mma_commit(bar_empty + s);
+                        if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
-                    tc::mma_commit(bar_empty + s);
-                    if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
-                if ((t + 1) % g.tpc == 0 || t == ntiles - 1) {
-                    tc::mma_commit(acc_full + (jc & 1));
-                    ++jc;
-                }
+                tc::mma_commit(acc_full + (jc & 1));
             }
         }
         __syncwarp();
