@@ -34,6 +34,8 @@ extern "C" {
 #define SCSFM_WITH_SSIM 1
 #define SCSFM_WITH_MASK 2
 #define SCSFM_WITH_AUTO_MASK 4
+/* scsfm_pairwise_fwd only: accumulate the masked sums but do not turn them into losses yet (scsfm_pairwise_finalize does) */
+#define SCSFM_DEFER_FINALIZE 0x100
 /* padding_mode of F.grid_sample (reference inverse_warp.py:262,267) */
 #define SCSFM_PAD_ZEROS 0
 #define SCSFM_PAD_BORDER 1
@@ -88,6 +90,14 @@ size_t scsfm_pairwise_stats_bytes(int njobs, int B);
 int scsfm_pairwise_fwd(const ScsfmPairJob* jobs_host, int njobs, const float* intrinsics, int B, int H, int W,
                        int flags, int padding_mode, void* stats, float* loss_out, const ScsfmPairMaps* maps_host,
                        void* stream);
+
+/* Second half of scsfm_pairwise_fwd(flags | SCSFM_DEFER_FINALIZE): mean_on_mask of every job (loss_functions.py:123-129) from
+ * the sums in stats[0 .. scsfm_pairwise_sums_count(njobs)) (doubles).  A data-parallel caller all-reduces (SUM) exactly that
+ * range over the ranks in between, so that the ratio of sums and the 10000-pixel threshold act on the GLOBAL batch as under the
+ * reference's DataParallel gather (train.py:168-169); grad_scale (= number of ranks, 1 otherwise) multiplies the backward
+ * scales because the gradient all-reduce that follows averages over the ranks. */
+int scsfm_pairwise_finalize(void* stats, int njobs, float grad_scale, float* loss_out, void* stream);
+int scsfm_pairwise_sums_count(int njobs);
 
 /* Backward of scsfm_pairwise_fwd: given d(loss)/d(photo) and d(loss)/d(geometry) (device scalars
  * grad_out[2]) accumulates gradients into jobs[i].grad_tgt_depth / grad_ref_depth / grad_pose.
@@ -275,6 +285,13 @@ int scsfm_act_bwd(float* d, const float* out, long long n, int act, void* stream
 /* pose head (PoseResNet.py:47-49): out[b,c] = scale * mean_hw x[b,hw,c]; backward broadcasts. */
 int scsfm_spatial_mean_fwd(const float* x, int B, int HW, int C, float scale, float* out, void* stream);
 int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale, float* dx, void* stream);
+
+/* Validation metrics (reference loss_functions.py:163-205, compute_errors): gt, pred [B,H,W]; per image the pixels inside the
+ * crop rows [y1,y2) x columns [x1,x2) with 0.1 < gt < max_depth; prediction clamped to [1e-3, max_depth] and scaled by
+ * median(gt) / median(pred) (lower medians, exact radix select).  out[b][8] = {abs_diff, abs_rel, sq_rel, a1, a2, a3,
+ * median(gt), median(pred)} (NaN for an empty mask); work: (2 * B) floats + B ints of scratch. */
+int scsfm_compute_errors(const float* gt, const float* pred, int B, int H, int W, int y1, int y2, int x1, int x2,
+                         float max_depth, void* work, float* out, void* stream);
 
 /* out[i] = round-to-nearest TF32 of in[i] (weights of the tensor-core convolutions, once per optimizer step) */
 int scsfm_round_tf32(const float* in, float* out, long long n, void* stream);

@@ -195,7 +195,10 @@ pairwise_fwd_kernel(PairJobs jobs, const float* __restrict__ Kmat, int B, int H,
 
 // mean_on_mask (loss_functions.py:123-129) for both terms of every job + the sum over jobs
 // (loss_functions.py:89-90).  Also stores the 1/sum(mask) scales the backward needs.
-__global__ void pairwise_finalize_kernel(double* stats, int njobs, float* __restrict__ loss_out) {
+// grad_scale multiplies the stored backward scales only (exact-global data-parallel mode: the sums were all-reduced over the
+// ranks, every rank back-propagates its own pixels' share of the GLOBAL loss and the averaged gradient all-reduce divides by
+// the number of ranks again).
+__global__ void pairwise_finalize_kernel(double* stats, int njobs, float* __restrict__ loss_out, double grad_scale) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double photo = 0.0, geo = 0.0;
     for (int j = 0; j < njobs; ++j) {
@@ -204,8 +207,8 @@ __global__ void pairwise_finalize_kernel(double* stats, int njobs, float* __rest
         // the reference evaluates sum(diff*mask)/sum(mask) in fp32
         const double sp = n3 > MIN_MASK_SUM ? 1.0 / n3 : 0.0;
         const double sg = n1 > MIN_MASK_SUM ? 1.0 / n1 : 0.0;
-        s[3] = sp;
-        s[4] = sg;
+        s[3] = sp * grad_scale;
+        s[4] = sg * grad_scale;
         s[5] = s[0] * sp;
         s[6] = s[2] * sg;
         photo += (double)(float)s[5];
@@ -650,10 +653,25 @@ extern "C" int scsfm_pairwise_fwd(const ScsfmPairJob* jobs_host, int njobs, cons
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, njobs * B);
     pairwise_fwd_kernel<<<grid, NTHREADS, 0, st>>>(pj, intrinsics, B, H, W, flags, padding_mode, (double*)stats, maps);
     SCSFM_CHECK_LAUNCH();
-    pairwise_finalize_kernel<<<1, 32, 0, st>>>((double*)stats, njobs, loss_out);
+    if (!(flags & SCSFM_DEFER_FINALIZE)) {
+        pairwise_finalize_kernel<<<1, 32, 0, st>>>((double*)stats, njobs, loss_out, 1.0);
+        SCSFM_CHECK_LAUNCH();
+    }
+    return SCSFM_OK;
+}
+
+// Second half of scsfm_pairwise_fwd when it was called with SCSFM_DEFER_FINALIZE: the caller may add the first
+// scsfm_pairwise_sums_count(njobs) doubles of `stats` (per job {sum photo, sum mask, sum geometry, ...}) over the ranks of a
+// data-parallel job in between, which makes mean_on_mask (loss_functions.py:123-129) and its 10000-pixel threshold act on the
+// GLOBAL batch exactly as the reference's DataParallel gather does.
+extern "C" int scsfm_pairwise_finalize(void* stats, int njobs, float grad_scale, float* loss_out, void* stream) {
+    SCSFM_CHECK_ARG(stats && loss_out && njobs >= 1 && njobs <= SCSFM_MAX_JOBS && grad_scale > 0.f, "pairwise_finalize: bad arguments");
+    pairwise_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((double*)stats, njobs, loss_out, (double)grad_scale);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
+
+extern "C" int scsfm_pairwise_sums_count(int njobs) { return njobs * STATS_PER_JOB; }
 
 extern "C" int scsfm_pairwise_bwd(const ScsfmPairJob* jobs_host, int njobs, const float* intrinsics, int B, int H, int W,
                                   int flags, int padding_mode, void* stats, const float* grad_out, void* stream) {

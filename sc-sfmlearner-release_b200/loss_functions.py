@@ -75,7 +75,8 @@ def compute_smooth_loss(tgt_depth, tgt_img, ref_depths, ref_imgs):
 @torch.no_grad()
 def compute_errors(gt, pred, dataset):
     """Validation metrics [abs_diff, abs_rel, sq_rel, a1, a2, a3] with the Garg (KITTI) / NYU crop and
-    per-image median scaling (reference :163-205).  Not on the per-iteration path."""
+    per-image median scaling (reference :163-205).  One median-select + one metrics launch for the whole batch
+    (csrc/eval_ops.cu); the only host synchronisation is the final read of the six numbers."""
     batch_size, h, w = gt.size()
     if dataset == "kitti":
         (ya, yb), (xa, xb), max_depth = (0.40810811, 0.99189189), (0.03594771, 0.96405229), 80
@@ -83,16 +84,5 @@ def compute_errors(gt, pred, dataset):
         (ya, yb), (xa, xb), max_depth = (0.09375, 0.98125), (0.0640625, 0.9390625), 10
     else:
         raise ValueError("dataset must be 'kitti' or 'nyu'")
-    crop = torch.zeros(h, w, dtype=torch.bool, device=gt.device)
-    crop[int(ya * h):int(yb * h), int(xa * w):int(xb * w)] = True
-    sums = torch.zeros(6, dtype=torch.float64, device=gt.device)
-    for g, p in zip(gt, pred):
-        keep = (g > 0.1) & (g < max_depth) & crop
-        vg = g[keep]
-        vp = p[keep].clamp(1e-3, max_depth)
-        vp = vp * torch.median(vg) / torch.median(vp)
-        ratio = torch.max(vg / vp, vp / vg)
-        err = (vg - vp).abs()
-        sums += torch.stack([err.mean(), (err / vg).mean(), (err * err / vg).mean(), (ratio < 1.25).float().mean(),
-                             (ratio < 1.25 ** 2).float().mean(), (ratio < 1.25 ** 3).float().mean()]).double()
-    return [v / batch_size for v in sums.tolist()]
+    per_image = _ops.compute_errors(gt, pred, int(ya * h), int(yb * h), int(xa * w), int(xb * w), float(max_depth))
+    return (per_image[:, :6].double().sum(0) / batch_size).tolist()

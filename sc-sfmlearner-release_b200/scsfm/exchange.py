@@ -43,6 +43,13 @@ class GradExchange:
             grad_arena.div_(self.world)
             self._works.append(dist.all_reduce(grad_arena, op=dist.ReduceOp.SUM, async_op=True))
 
+    def allreduce_sums(self, t):
+        """In-place SUM over the ranks of a small tensor on the current stream (the masked sums of the losses in the
+        exact-global mode: a handful of doubles; stream-ordered, no host synchronisation)."""
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
     def pending(self):
         return len(self._works)
 

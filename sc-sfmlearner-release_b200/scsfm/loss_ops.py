@@ -38,13 +38,16 @@ class PhotoGeoLoss(torch.autograd.Function):
     """compute_photo_and_geometry_loss (reference loss_functions.py:50-92) as one fused op.
 
     apply(cfg, tgt_img, intrinsics, *ref_imgs, *tgt_depth[s], *ref_depths[i][s], *poses, *poses_inv)
-    with cfg = (n_ref, n_scales, flags, padding, bidir); bidir=False evaluates only the tgt<-ref
-    direction (compute_pairwise_loss).  Returns (photo_loss, geometry_loss).
+    with cfg = (n_ref, n_scales, flags, padding, bidir[, sums_allreduce, world]); bidir=False evaluates only the
+    tgt<-ref direction (compute_pairwise_loss).  sums_allreduce (data-parallel "exact global masks" option): callable
+    that sums a float64 device tensor over the ranks in place -- the masked sums of every pair-direction are reduced
+    before mean_on_mask, so the loss and its 10000-pixel threshold are those of the GLOBAL batch (what the reference
+    computes after its DataParallel gather).  Returns (photo_loss, geometry_loss).
     """
 
     @staticmethod
     def _jobs(cfg, tgt_img, ref_imgs, tgt_depth, ref_depths, poses, poses_inv, grads=None):
-        n_ref, n_scales, _, _, bidir = cfg
+        n_ref, n_scales, bidir = cfg[0], cfg[1], cfg[4]
         H, W = tgt_img.shape[-2:]
         jobs = []
         for i in range(n_ref):
@@ -79,7 +82,8 @@ class PhotoGeoLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, tgt_img, intrinsics, *tensors):
         lib = L.load()
-        n_ref, n_scales, flags, padding, _ = cfg
+        n_ref, n_scales, flags, padding = cfg[:4]
+        sums_allreduce, world = (cfg[5], cfg[6]) if len(cfg) > 5 and cfg[5] is not None else (None, 1)
         tgt_img = L.dev_f32(tgt_img, "tgt_img")
         intrinsics = L.dev_f32(intrinsics, "intrinsics")
         tensors = [L.dev_f32(t, "loss input") for t in tensors]
@@ -94,8 +98,14 @@ class PhotoGeoLoss(torch.autograd.Function):
             st = torch.empty(lib.scsfm_pairwise_stats_bytes(len(chunk), B) // 8, device=tgt_img.device,
                              dtype=torch.float64)
             arr = (L.PairJob * len(chunk))(*chunk)
+            defer = 0x100 if sums_allreduce is not None else 0          # SCSFM_DEFER_FINALIZE
             L.launch(lib.scsfm_pairwise_fwd, "scsfm_pairwise_fwd", "pair_fwd", 2, 32.0 * len(chunk) * B * H * W, arr, len(chunk),
-                     L.ptr(intrinsics), B, H, W, flags, padding, L.ptr(st), L.ptr(part), None, L.stream())
+                     L.ptr(intrinsics), B, H, W, flags | defer, padding, L.ptr(st), L.ptr(part), None, L.stream())
+            if sums_allreduce is not None:
+                sums_allreduce(st[:lib.scsfm_pairwise_sums_count(len(chunk))])
+                lib.scsfm_pairwise_finalize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+                L.launch(lib.scsfm_pairwise_finalize, "scsfm_pairwise_finalize", "pair_fwd", 1, 0.0, L.ptr(st), len(chunk), float(world),
+                         L.ptr(part), L.stream())
             out = out + part if len(jobs) > L.MAX_JOBS else part
             stats.append(st)
         ctx.cfg = cfg
@@ -107,7 +117,7 @@ class PhotoGeoLoss(torch.autograd.Function):
     def backward(ctx, g_photo, g_geo):
         lib = L.load()
         cfg = ctx.cfg
-        n_ref, n_scales, flags, padding, _ = cfg
+        n_ref, n_scales, flags, padding = cfg[:4]
         tgt_img, intrinsics, *tensors = ctx.saved_tensors
         ref_imgs, tgt_depth, ref_depths, poses, poses_inv = PhotoGeoLoss._split(cfg, tensors)
         B, _, H, W = tgt_img.shape
@@ -130,10 +140,10 @@ class PhotoGeoLoss(torch.autograd.Function):
 
 
 def photo_and_geometry_loss(tgt_img, ref_imgs, intrinsics, tgt_depth, ref_depths, poses, poses_inv, max_scales,
-                            with_ssim, with_mask, with_auto_mask, padding_mode):
+                            with_ssim, with_mask, with_auto_mask, padding_mode, sums_allreduce=None, world=1):
     n_scales = min(len(tgt_depth), max_scales)
     n_ref = min(len(ref_imgs), len(ref_depths), len(poses), len(poses_inv))   # zip() semantics of the reference
-    cfg = (n_ref, n_scales, _flags(with_ssim, with_mask, with_auto_mask), _padding(padding_mode), True)
+    cfg = (n_ref, n_scales, _flags(with_ssim, with_mask, with_auto_mask), _padding(padding_mode), True, sums_allreduce, world)
     if n_ref == 0 or n_scales == 0:
         return 0, 0
     flat = (list(ref_imgs[:n_ref]) + list(tgt_depth[:n_scales]) +
@@ -266,4 +276,21 @@ def pose_vec2mat(vec, rotation_mode="euler"):
     out = torch.empty(vec.shape[0], 3, 4, device=vec.device, dtype=torch.float32)
     L.check(lib.scsfm_pose_vec2mat(L.ptr(vec), vec.shape[0], 0 if rotation_mode == "euler" else 1, L.ptr(out),
                                    L.stream()), "scsfm_pose_vec2mat")
+    return out
+
+
+def compute_errors(gt, pred, y1, y2, x1, x2, max_depth):
+    """Per-image validation metrics [B,8] = {abs_diff, abs_rel, sq_rel, a1, a2, a3, median(gt), median(pred)} (scsfm_compute_errors)."""
+    gt, pred = L.dev_f32(gt, "gt"), L.dev_f32(pred, "pred")
+    if gt.dim() != 3 or gt.shape != pred.shape:
+        raise ValueError("compute_errors expects gt and pred of shape [B,H,W], got %s and %s" % (tuple(gt.shape), tuple(pred.shape)))
+    B, H, W = gt.shape
+    lib = L.load()
+    lib.scsfm_compute_errors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    out = torch.empty(B, 8, device=gt.device, dtype=torch.float32)
+    work = torch.empty(3 * B, device=gt.device, dtype=torch.float32)
+    L.launch(lib.scsfm_compute_errors, "scsfm_compute_errors", "eval", 2, 5 * 8.0 * gt.numel(), L.ptr(gt), L.ptr(pred), B, H, W, y1, y2, x1, x2,
+             max_depth, L.ptr(work), L.ptr(out), L.stream())
     return out

@@ -33,7 +33,8 @@ class Trainer:
     """Holds the two networks, the fused Adam and (optionally) the data-parallel gradient exchange."""
 
     def __init__(self, disp_net, pose_net, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.0, num_scales=1, with_ssim=1,
-                 with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None, conv_mode=None):
+                 with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None, conv_mode=None,
+                 exact_global_masks=False):
         self.disp_net, self.pose_net = disp_net, pose_net
         if conv_mode is not None:           # "fp32" | "tf32" | "tf32x3" (nnops.MODES); None keeps each network's own setting
             disp_net.set_conv_mode(conv_mode)
@@ -47,6 +48,12 @@ class Trainer:
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.exchange = None
+        # data parallel only.  False (default): standard DDP semantics -- every rank is the reference at batch B/N and the
+        # gradients are averaged.  True: the masked sums of mean_on_mask (loss_functions.py:123-129) are all-reduced (one
+        # tiny SUM of 8 doubles per pair-direction) before the losses are formed, so the photometric / geometry losses, their
+        # 10000-pixel thresholds and therefore the gradients are those of the GLOBAL batch -- exactly what the reference's
+        # nn.DataParallel computes on the gathered outputs (per-GPU BatchNorm, global loss; train.py:168-169).
+        self.exact_global_masks = bool(exact_global_masks)
         self._graph = None
         self.launches_per_step = None
         if self.distributed:
@@ -62,9 +69,15 @@ class Trainer:
         tgt_depth, ref_depths = compute_depth(self.disp_net, tgt_img, ref_imgs)
         poses, poses_inv = compute_pose_with_inv(self.pose_net, tgt_img, ref_imgs)
         c = self.cfg
-        photo, geo = LF.compute_photo_and_geometry_loss(tgt_img, ref_imgs, intrinsics, tgt_depth, ref_depths, poses,
-                                                        poses_inv, c["num_scales"], c["with_ssim"], c["with_mask"],
-                                                        c["with_auto_mask"], c["padding_mode"])
+        if self.exchange is not None and self.exact_global_masks:
+            from . import loss_ops
+            photo, geo = loss_ops.photo_and_geometry_loss(tgt_img, ref_imgs, intrinsics, tgt_depth, ref_depths, poses, poses_inv,
+                                                          c["num_scales"], c["with_ssim"], c["with_mask"], c["with_auto_mask"],
+                                                          c["padding_mode"], self.exchange.allreduce_sums, self.world)
+        else:
+            photo, geo = LF.compute_photo_and_geometry_loss(tgt_img, ref_imgs, intrinsics, tgt_depth, ref_depths, poses,
+                                                            poses_inv, c["num_scales"], c["with_ssim"], c["with_mask"],
+                                                            c["with_auto_mask"], c["padding_mode"])
         smooth = LF.compute_smooth_loss(tgt_depth, tgt_img, ref_depths, ref_imgs)
         w1, w2, w3 = self.w
         return w1 * photo + w2 * smooth + w3 * geo, photo, smooth, geo

@@ -179,7 +179,8 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind, mod
         assert isinstance(outs, list) and len(outs) == 4
         loss = sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(outs))
         for s, o in enumerate(outs):
-            np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"{tag}_out_s{s}"], rtol=5e-4, atol=5e-5)
+            assert rel_l2(o.detach(), g[f"{tag}_out_s{s}"]) < 1e-4
+            np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"{tag}_out_s{s}"], rtol=2e-3, atol=5e-5)
     else:
         o = net(img1.to(DEV), img2.to(DEV))
         loss = (o * torch.arange(1, 7, dtype=o.dtype, device=DEV)).sum() * 100
@@ -196,30 +197,36 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind, mod
             assert float(v.abs().max()) == 0.0, k
     # element-wise gradients against the fp64 oracle run on the same weights; the yardstick is the error the
     # fp32 CPU oracle itself makes against fp64 (deep nets with tiny BatchNorm populations amplify fp32 noise)
-    def oracle_grads(dtype):
-        ref = (N.DispResNet(layers) if kind == "disp" else N.PoseResNet(layers)).to(dtype)
-        ref.load_state_dict({k: v.to(dtype) for k, v in det_weights(ref.state_dict()).items()})
+    def oracle_grads(dtype, dev="cpu"):
+        ref = (N.DispResNet(layers) if kind == "disp" else N.PoseResNet(layers)).to(dtype).to(dev)
+        ref.load_state_dict({k: v.to(dtype).to(dev) for k, v in det_weights(ref.state_dict()).items()})
         ref.train()
         if kind == "disp":
-            ro = ref(img1.to(dtype))
+            ro = ref(img1.to(dtype).to(dev))
             rl = sum(((1.0 / o) * (i + 1)).mean() for i, o in enumerate(ro))
         else:
-            ro = ref(img1.to(dtype), img2.to(dtype))
-            rl = (ro * torch.arange(1, 7, dtype=ro.dtype)).sum() * 100
+            ro = ref(img1.to(dtype).to(dev), img2.to(dtype).to(dev))
+            rl = (ro * torch.arange(1, 7, dtype=ro.dtype, device=dev)).sum() * 100
         rl.backward()
         return {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
-    g64, g32 = oracle_grads(torch.float64), oracle_grads(torch.float32)
+    # Yardstick = what INDEPENDENT fp32 evaluations of the same network do against fp64: the CPU oracle and stock PyTorch / cuDNN on
+    # this GPU with TF32 off.  These deliberately ill-conditioned test networks (random weights, BatchNorm over 12 samples at the
+    # deepest stage) amplify fp32 rounding by 1e2..1e4 and a single ReLU / max-pool decision that flips on a ~0 activation moves
+    # every upstream gradient at once: the round-1 "ResNet-50 drift" (1.5e-3 vs 1.5e-4) was exactly that -- tools/diag_grad_error.py
+    # shows the CPU oracle itself at 4.4e-3 on another run (profiles/r02_diag_disp50_fp32.txt).  Hence two yardsticks, no per-depth slack.
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g64, g32, g32gpu = oracle_grads(torch.float64), oracle_grads(torch.float32), oracle_grads(torch.float32, DEV)
     errs = sorted((rel_l2(grads[k], gr), k) for k, gr in g64.items())
-    errs_ref = sorted(rel_l2(g32[k], gr) for k, gr in g64.items())
+    errs_cpu = sorted(rel_l2(g32[k], gr) for k, gr in g64.items())
+    errs_gpu = sorted(rel_l2(g32gpu[k], gr) for k, gr in g64.items())
     med, worst = errs[len(errs) // 2][0], errs[-1]
-    print(tag, mode, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle's own: median %.2e worst %.2e"
-          % (med, worst[0], worst[1], errs_ref[len(errs_ref) // 2], errs_ref[-1]))
-    # systematic accuracy = the median (must be fp32-noise level); individual parameters may see a ReLU/ELU gate flip on an
-    # activation that is ~0 in one evaluation and ~-0 in the other (any independent fp32 evaluation does), hence the looser worst bound
-    # ResNet-50 DispResNet: measured median 1.5e-3 vs the fp32 CPU oracle's 1.5e-4 on this 64x96 random-weight net (BatchNorm over 12
-    # samples at the deepest stage); open item in DESIGN.md -- the bound below is looser for num_layers 50 until it is understood
-    slack = 3 if layers == 18 else 15
-    assert med < slack * errs_ref[len(errs_ref) // 2] + 1e-4 and worst[0] < slack * errs_ref[-1] + 3e-2
+    yard_med = max(errs_cpu[len(errs_cpu) // 2], errs_gpu[len(errs_gpu) // 2])
+    yard_worst = max(errs_cpu[-1], errs_gpu[-1])
+    print(tag, mode, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle: median %.2e worst %.2e; "
+          "stock PyTorch/cuDNN fp32 on this GPU: median %.2e worst %.2e"
+          % (med, worst[0], worst[1], errs_cpu[len(errs_cpu) // 2], errs_cpu[-1], errs_gpu[len(errs_gpu) // 2], errs_gpu[-1]))
+    assert med < 4 * yard_med + 1e-4 and worst[0] < 4 * yard_worst + 1e-3
     sd2 = net.state_dict()
     rn = np.array([float(sd2[k].double().norm()) for k in g[f"{tag}_running_names"]])
     np.testing.assert_allclose(rn, g[f"{tag}_running_norms"], rtol=1e-4)
