@@ -354,8 +354,7 @@ def run_ours(args):
         del t2
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     is_conv = dominant.startswith("conv")
     if is_conv:
@@ -419,9 +418,21 @@ def run_ours(args):
         line["gpu_reference"] = gref
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, cfg, steps=2, warmup=1, budget_s=30.0)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """End of a multi-rank run.  The captured CUDA graphs hold NCCL kernels: tearing the process group down with them alive
+    hangs in the NCCL watchdog (observed on 2 GPUs: the line was printed, then destroy_process_group blocked until the
+    10-minute watchdog abort).  All results are out, so leave without the teardown."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # --------------------------------------------------------------------------------------------------
