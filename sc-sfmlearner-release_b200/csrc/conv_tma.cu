@@ -52,6 +52,10 @@ struct TmaGeom {
     // split-accumulate passes per (channel chunk, dx): pass i multiplies (activations: lo if a_lo bit i else raw) by
     // (weights: lo if w_lo bit i else raw); plain TF32 = one pass with both masks 0
     int npass, a_lo, w_lo;
+    // split mode with <= 64 output channels: the weight tile stacks W (rows 0..) and lo(W) (rows 64..) on the M side of ONE
+    // tcgen05.mma, so the two passes lo(x) and x produce all four products (TMEM lanes c and 64 + c are added in the epilogue):
+    // two MMAs per K8 slice instead of three
+    int stack;
     // accumulation chunks: the tensor core adds into the TMEM accumulator with truncation (measured: relative error ~ 3e-8 per
     // tcgen05.mma of the chain, a systematic bias), so a chain is cut after `cpg` channel chunks (~100 MMAs) and the epilogue
     // warps add the partial accumulators in registers (round-to-nearest).  cpg >= chunks: one chain per tile (plain TF32 mode).
@@ -70,7 +74,7 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                 const __grid_constant__ CUtensorMap amap_lo, const __grid_constant__ CUtensorMap wmap_lo) {
     constexpr int NPIX = MT * TBM;                           // TMEM columns of one accumulator buffer
     constexpr int TMEM_COLS = 2 * NPIX;                      // 256 or 512
-    constexpr int W_TILE = BNW * 128;                         // one tap: BNW rows x 32 floats
+    const int W_TILE = g.stack ? TBM * 128 : BNW * 128;      // one tap: BNW rows x 32 floats (stacked: W at row 0, lo(W) at row 64)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // barriers live in FRONT of the stage ring: the MMA's 128-row read of a BNW-row weight tile may run past the last stage
@@ -81,7 +85,7 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint8_t* ring = smem + 1024;
     // epilogue transpose buffer T[64 pixels][BNW + 4] behind the ring and the over-read pad
-    float* T = reinterpret_cast<float*>(ring + (size_t)g.stages * g.stage_bytes + (TBM - BNW) * 128);
+    float* T = reinterpret_cast<float*>(ring + (size_t)g.stages * g.stage_bytes + (g.stack ? 0 : (TBM - BNW) * 128));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
@@ -114,7 +118,7 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             tc::tma_prefetch_desc(&wmap);
             if (g.a_lo) tc::tma_prefetch_desc(&amap_lo);
             if (g.w_lo) tc::tma_prefetch_desc(&wmap_lo);
-            const uint32_t tx_bytes = (uint32_t)(patch_rows * TW * 128 + v.kh * W_TILE);
+            const uint32_t tx_bytes = (uint32_t)(patch_rows * TW * 128 + v.kh * (g.stack ? 2 : 1) * BNW * 128);
             int s = 0;
             uint32_t ph = 0;
             long long t_wait = 0;
@@ -142,9 +146,16 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                             const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
                             tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
                             tc::tma_load_4d(st, am, ck * TBK, x0 + dx, y0, b, bar_full + s);
-                            for (int dy = 0; dy < v.kh; ++dy)
-                                tc::tma_load_2d(st + (uint32_t)(g.a_bytes + dy * W_TILE), wm, (dy * v.kw + dx) * p.Cin + ck * TBK, n0,
-                                                bar_full + s);
+                            for (int dy = 0; dy < v.kh; ++dy) {
+                                const uint32_t wdst = st + (uint32_t)(g.a_bytes + dy * W_TILE);
+                                const int kcol = (dy * v.kw + dx) * p.Cin + ck * TBK;
+                                if (g.stack) {
+                                    tc::tma_load_2d(wdst, &wmap, kcol, n0, bar_full + s);
+                                    tc::tma_load_2d(wdst + 64 * 128, &wmap_lo, kcol, n0, bar_full + s);
+                                } else {
+                                    tc::tma_load_2d(wdst, wm, kcol, n0, bar_full + s);
+                                }
+                            }
                             if (++s == g.stages) { s = 0; ph ^= 1; }
                         }
                     }
@@ -250,7 +261,8 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             const int b = t / g.tiles_y;
             const int y0 = ty * (MT * TH), x0 = tx * TW;
             const int cv = min(TBM, N - n0);                     // real channels of this Cout tile (multiple of 4)
-            const bool loader = quarter * 32 < cv;                // warp-uniform: this lane quarter holds real channels
+            // warp-uniform: this lane quarter holds real channels (stacked: quarters 2, 3 hold the lo(W) products of channels 0..63)
+            const bool loader = (g.stack ? (quarter & 1) : quarter) * 32 < cv;
             // ---- drain the tile's accumulation chains into registers (TMEM -> registers, fp32 round-to-nearest adds)
             for (int c = 0; c < nchains; ++c, ++jc) {
                 const int buf = jc & 1;
@@ -297,8 +309,9 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
             for (int rd = 0; rd < RPT; ++rd) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // A: everybody has finished reading the previous round
                 if (loader) {
-                    float* dst = T + (32 * half) * TS + quarter * 32 + lane;
-                    if (quarter * 32 + lane < CT) {            // (a 16-channel tile only has 16 real lanes)
+                    const int tq = g.stack ? (quarter & 1) : quarter, plane = g.stack ? (quarter >> 1) : 0;
+                    float* dst = T + plane * (64 * TS) + (32 * half) * TS + tq * 32 + lane;
+                    if (tq * 32 + lane < CT) {            // (a 16-channel tile only has 16 real lanes)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dst[i * TS] = accr[rd][i];     // consecutive lanes = consecutive words
                     }
@@ -311,6 +324,10 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
                     const int row = l >> g.tw_log2, col = l & (TW - 1);
                     if (ch_ok && y0 + row < Ho && x0 + col < Wo) {
                         float4 x = *reinterpret_cast<const float4*>(T + px * TS + 4 * c4);
+                        if (g.stack) {                          // + the lo(W) products from TMEM lanes 64 + c
+                            const float4 x2 = *reinterpret_cast<const float4*>(T + 64 * TS + px * TS + 4 * c4);
+                            x.x += x2.x; x.y += x2.y; x.z += x2.z; x.w += x2.w;
+                        }
                         x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
                         const long long off = tile_off + (long long)row * row_step + (long long)col * px_step;
                         if (p.addend != nullptr) {
@@ -399,10 +416,12 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
     g.n_tiles = (p.Cout + TBM - 1) / TBM;
     g.num_work = g.tiles_x * g.tiles_y * p.B * g.n_tiles;
     g.a_bytes = ((MT * TH + v.kh - 1) * TW * 128 + 1023) / 1024 * 1024;
-    g.stage_bytes = g.a_bytes + v.kh * BNW * 128;
+    // split mode with a single <= 64-channel Cout tile: W and lo(W) stacked on the M side (see TmaGeom.stack)
+    g.stack = (BNW <= 64 && p.Cout <= 64 && p.in_lo != nullptr && p.w_lo != nullptr) ? 1 : 0;
+    g.stage_bytes = g.a_bytes + v.kh * (g.stack ? TBM : BNW) * 128;
     // 1024 alignment slack + 1024 barrier block + ring + the MMA's over-read past a BNW-row weight tile (M = 128 rows) +
-    // the epilogue's transpose buffer T[64][BNW + 4]
-    const int fixed = 1024 + 1024 + (TBM - BNW) * 128 + 64 * (BNW + 4) * 4;
+    // the epilogue's transpose buffer T[64][BNW + 4] (two planes when stacked)
+    const int fixed = 1024 + 1024 + (g.stack ? 0 : (TBM - BNW) * 128) + (g.stack ? 2 : 1) * 64 * (BNW + 4) * 4;
     g.stages = (TMA_SMEM_MAX - fixed) / g.stage_bytes;
     if (g.stages > TMA_MAX_STAGES) g.stages = TMA_MAX_STAGES;
     if (g.stages < 2) {
@@ -413,7 +432,7 @@ static int launch_tma_cfg(const ScsfmConv& p, const TcView& v, int tw_log2, cuda
     // split-accumulate passes: raw x raw, then lo(activations) x raw(weights), then raw(activations) x lo(weights)
     g.npass = 1; g.a_lo = 0; g.w_lo = 0;
     if (p.in_lo != nullptr) { g.a_lo |= 1 << g.npass; ++g.npass; }
-    if (p.w_lo != nullptr) { g.w_lo |= 1 << g.npass; ++g.npass; }
+    if (p.w_lo != nullptr && !g.stack) { g.w_lo |= 1 << g.npass; ++g.npass; }
     {
         const int chunks = (p.Cin + TBK - 1) / TBK;
         const int mma_per_chunk = v.kw * g.npass * v.kh * (TBK / 8);

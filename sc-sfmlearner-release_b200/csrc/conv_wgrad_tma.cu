@@ -36,6 +36,8 @@ struct WtGeom {
     int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4)
     int stages, patch_bytes, stage_bytes;
     int npass, x_lo, d_lo;       // split-accumulate passes per tile: pass i uses lo(input) if x_lo bit i, lo(dout) if d_lo bit i
+    int stack;                   // split mode, Cout <= 64: dout in atoms 0-1 and lo(dout) in atoms 2-3 of the M-side tile, so the passes
+                                 // lo(x) and x give all four products (lanes o and 64 + o both red.add into dw): 2 MMAs instead of 3
     int tpc;                     // pixel tiles per accumulation chain: the tensor core adds into TMEM with truncation (bias ~3e-8 per
                                  // MMA of a chain), so the epilogue warps drain the accumulator into registers (round-to-nearest adds)
                                  // every tpc tiles while the MMAs continue in the second TMEM buffer
@@ -89,7 +91,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             tc::tma_prefetch_desc(&dmap);
             const int prows = TH + p.kh - 1;
             const uint32_t row_bytes = (uint32_t)(TW * 128);
-            const uint32_t tx_bytes = (uint32_t)(g.atoms_m * TBM * 128) + (uint32_t)(prows * g.G) * row_bytes;
+            const uint32_t tx_bytes = (uint32_t)((g.stack ? 2 : 1) * g.atoms_m * TBM * 128) + (uint32_t)(prows * g.G) * row_bytes;
             int s = 0;
             uint32_t ph = 0;
             // one accumulation chain = tpc tiles; inside a chain the low-part passes run first, the raw x raw pass last
@@ -108,8 +110,14 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                     const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
                     tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
                     // M side: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
-                    for (int a = 0; a < g.atoms_m; ++a)
-                        tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                    for (int a = 0; a < g.atoms_m; ++a) {
+                        if (g.stack) {
+                            tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
+                            tc::tma_load_4d(st + (uint32_t)((2 + a) * TBM * 128), &dmap_lo, n0 + 32 * a, x0, y0, b, bar_full + s);
+                        } else {
+                            tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                        }
+                    }
                     // N side: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
                     const uint32_t pst = st + WT_DOUT_BYTES;
                     for (int r = 0; r < prows; ++r)
@@ -160,9 +168,10 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     } else {
         // ------------------------------------------------------------------ epilogue: dw[o][(dy, dx, channel)] += D[o][...]
         const int quarter = warp & 3, half = warp >> 2;
-        const int o = n0 + quarter * 32 + lane;
+        const int oq = g.stack ? (quarter & 1) : quarter; // stacked: lane quarters 2, 3 hold the lo(dout) products of channels 0..63
+        const int o = n0 + oq * 32 + lane;
         const int Mtot = p.kh * p.kw * p.Cin;
-        const bool real = n0 + quarter * 32 < p.Cout;     // warp-uniform: this lane quarter holds real output channels
+        const bool real = n0 + oq * 32 < p.Cout;          // warp-uniform: this lane quarter holds real output channels
         constexpr int APW = 3;                            // accumulator atoms (32 columns) per warp: a = half + 2 * ai < kh * G <= 6
         float accr[APW][32];
         const int nchains = (ntiles + g.tpc - 1) / g.tpc;
@@ -257,8 +266,9 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     g.tiles_per_split = (g.tiles_total + splits - 1) / splits;
     splits = (g.tiles_total + g.tiles_per_split - 1) / g.tiles_per_split;
     g.npass = 1; g.x_lo = 0; g.d_lo = 0;
+    g.stack = (p.Cout <= 64 && p.in_lo != nullptr && p.dout_lo != nullptr) ? 1 : 0;
     if (p.in_lo != nullptr) { g.x_lo |= 1 << g.npass; ++g.npass; }
-    if (p.dout_lo != nullptr) { g.d_lo |= 1 << g.npass; ++g.npass; }
+    if (p.dout_lo != nullptr && !g.stack) { g.d_lo |= 1 << g.npass; ++g.npass; }
     // split mode: chains of <= 96 MMAs (16 per tile and pass); plain TF32: one chain per CTA
     g.tpc = g.npass > 1 ? (96 / (16 * g.npass) > 0 ? 96 / (16 * g.npass) : 1) : g.tiles_per_split;
     CUtensorMap xmap, dmap, xmap_lo, dmap_lo;
