@@ -55,7 +55,7 @@ def back_project(depth, K_inv):
     module-global pixel grid cache (inverse_warp.py:5,39-40): the grid is rebuilt.
     """
     B, H, W = depth.shape
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=depth.dtype), torch.arange(W, dtype=depth.dtype),
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=depth.dtype, device=depth.device), torch.arange(W, dtype=depth.dtype, device=depth.device),
                             indexing="ij")
     pix = torch.stack([xs, ys, torch.ones_like(xs)], 0).view(1, 3, -1).expand(B, 3, -1)
     rays = (K_inv @ pix).view(B, 3, H, W)

