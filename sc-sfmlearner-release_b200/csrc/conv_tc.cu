@@ -326,7 +326,9 @@ struct WgCfg {
 // BORDER = true (used after the zero-padding TMA weight-gradient kernel on a reflection-padded layer): the K dimension only
 // runs over the 2*(Ho+Wo)-4 border pixels of every image and only the taps that fall OUTSIDE the image contribute, read
 // at their reflected positions -- exactly the part of the gradient the zero-padded pass left out.
-template <int BN, bool BORDER = false>
+// STACK = true (split mode, Cout <= BN / 2): the N-side tile holds dout in columns [0, BN/2) and lo(dout) in [BN/2, BN), so the two
+// passes lo(in) and in give all four products (columns o and BN/2 + o are both added into dw[o]): 2 passes instead of 3.
+template <int BN, bool BORDER = false, bool STACK = false>
 __global__ void __launch_bounds__(FW_THREADS)
 conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     using Cfg = WgCfg<BN>;
@@ -348,7 +350,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     const int KB = (pix_end - pix_begin + 31) / 32;
     if (KB <= 0) return;
     // split-accumulate passes over the CTA's pixel range (ScsfmConv.in_lo / dout_lo): raw x raw, lo(in) x raw(dout), raw(in) x lo(dout)
-    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
+    const int npass = STACK ? 2 : 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -389,7 +391,9 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         constexpr int B_IT = (32 * BCH) / (FW_PWARPS * 32);  // per-thread chunk loads: 1, 2, 4
         constexpr int B_STEP = (FW_PWARPS * 32) / BCH;       // pixel-row step between a thread's B chunks
         const int b_c4 = tid % BCH, b_kr0 = tid / BCH;
-        const int nn = n0 + 4 * b_c4;
+        // stacked: chunk columns >= BN/2 read lo(dout) at channel (column - BN/2)
+        const bool b_lo_half = STACK && 4 * b_c4 >= BN / 2;
+        const int nn = STACK ? (4 * b_c4 - (b_lo_half ? BN / 2 : 0)) : n0 + 4 * b_c4;
         const bool b_ok = nn < N;
         const uint32_t b_smem = tc::smem_u32(sB) + (uint32_t)((b_c4 >> 3) * 512);
         // pixel (b, ho, wo) of this thread's first A row in the current k-block, advanced by 32 per block
@@ -398,7 +402,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         for (int q = 0; q < npass; ++q) {
         const int ps = (q + 1) % npass;              // low-part passes first (added while the accumulators are small), raw x raw last
         const float* a_base = (ps == 1 && p.in_lo != nullptr) ? p.in_lo : p.in;
-        const float* b_base = (ps == npass - 1 && ps > 0 && p.dout_lo != nullptr) ? p.dout_lo : p.dout;
+        const float* b_base = STACK ? (b_lo_half ? p.dout_lo : p.dout)
+                                    : ((ps == npass - 1 && ps > 0 && p.dout_lo != nullptr) ? p.dout_lo : p.dout);
         {
             const int px = pix_begin + PPT * kq;
             pb = px / (p.Ho * p.Wo);
@@ -479,7 +484,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
             if (row < Mtot) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int o = n0 + cc * 32 + j;
+                    const int col = cc * 32 + j;
+                    const int o = STACK ? (col >= BN / 2 ? col - BN / 2 : col) : n0 + col;
                     if (o < N) red_add(p.dw + (size_t)o * Mtot + row, __uint_as_float(r[j]));
                 }
             }
@@ -533,18 +539,18 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t ra
 
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st);   // conv_simt.cu
 
-template <int BN, bool BORDER = false>
+template <int BN, bool BORDER = false, bool STACK = false>
 static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     using Cfg = WgCfg<BN>;
-    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, BORDER, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     SCSFM_CHECK_CUDA(attr_rc);
     const int Mtot = p.kh * p.kw * p.Cin, npix = p.B * (BORDER ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
-    const int mt = (Mtot + TBM - 1) / TBM, nt = (p.Cout + BN - 1) / BN;
+    const int mt = (Mtot + TBM - 1) / TBM, nt = STACK ? 1 : (p.Cout + BN - 1) / BN;
     int splits = (148 * 3 + mt * nt - 1) / (mt * nt);          // 3 CTAs per SM fit
     const int max_splits = (npix + 1023) / 1024;             // at least 32 k-blocks per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
+    const int npass = STACK ? 2 : 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
     if (npass > 1) {
         // split-accumulate (parity) mode: bound every accumulation chain to ~160 tcgen05.mma (truncation bias ~5e-6):
         // chain = k-blocks * 4 MMAs * passes / NACC.  More, shorter CTAs; their partial tiles are added with fp32 atomics (RN)
@@ -554,7 +560,7 @@ static int launch_wgrad_tc(const ScsfmConv& p, cudaStream_t st) {
     }
     const int pps = ((npix + splits - 1) / splits + 31) / 32 * 32;
     dim3 grid(mt, nt, (npix + pps - 1) / pps);
-    conv_wgrad_tc_kernel<BN, BORDER><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
+    conv_wgrad_tc_kernel<BN, BORDER, STACK><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, pps);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -824,7 +830,9 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
             else if (p->Cout <= 64) rc = launch_wgrad_tc<64, true>(*p, st);
             else rc = launch_wgrad_tc<128, true>(*p, st);
         }
-    } else if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
+    } else if (p->in_lo != nullptr && p->dout_lo != nullptr && p->Cout <= 16) rc = launch_wgrad_tc<32, false, true>(*p, st);
+    else if (p->in_lo != nullptr && p->dout_lo != nullptr && p->Cout <= 32) rc = launch_wgrad_tc<64, false, true>(*p, st);
+    else if (p->Cout <= 32) rc = launch_wgrad_tc<32>(*p, st);
     else if (p->Cout <= 64) rc = launch_wgrad_tc<64>(*p, st);
     else rc = launch_wgrad_tc<128>(*p, st);
     if (rc) return rc;

@@ -257,12 +257,29 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
         set_error("conv_wgrad_tma: stage of %d bytes does not fit twice in shared memory", g.stage_bytes);
         return SCSFM_ERR_ARG;
     }
-    // split the pixel tiles so that about two waves of CTAs exist, with at least 8 tiles per CTA
+    // Split the pixel tiles over gridDim.z.  One CTA per SM is resident (shared memory), so the kernel takes
+    //   waves * (tiles per CTA + fixed cost per CTA)   with waves = ceil(slices * splits / SMs):
+    // pick the split count that minimises it (the former "about two waves" rule gave e.g. 297 CTAs = 2.007 waves on 148 SMs,
+    // i.e. three waves of 13 tiles where one wave of 26 would do).  The fixed cost (prologue + red.add epilogue of a
+    // 128 x 192 partial tile) is worth about 3 tiles; at least 2 tiles per CTA.
     const int slices = g.groups * p.kw * nt;
-    int splits = (2 * 148 + slices - 1) / slices;
-    const int max_splits = (g.tiles_total + 7) / 8;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    int nsm = 148;
+    {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) nsm = v;
+    }
+    int splits = 1;
+    {
+        const int max_splits = g.tiles_total >= 2 ? g.tiles_total / 2 : 1;
+        long best = -1;
+        for (int sp = 1; sp <= max_splits && sp <= 4096; ++sp) {
+            const int tps = (g.tiles_total + sp - 1) / sp;
+            const int real = (g.tiles_total + tps - 1) / tps;
+            const long waves = ((long)slices * real + nsm - 1) / nsm;
+            const long cost = waves * (tps + 3);
+            if (best < 0 || cost < best) { best = cost; splits = real; }
+        }
+    }
     g.tiles_per_split = (g.tiles_total + splits - 1) / splits;
     splits = (g.tiles_total + g.tiles_per_split - 1) / g.tiles_per_split;
     g.npass = 1; g.x_lo = 0; g.d_lo = 0;
