@@ -257,13 +257,13 @@ int scsfm_bn_prepare(const double* sums, int groups, int C, long long count_per_
  * sums -- also writes `saved` and updates the running statistics like scsfm_bn_prepare; eval (sums == NULL) from the
  * running statistics.  flags: bit 0 = ReLU, SCSFM_ROUND_TF32 = round the result. */
 int scsfm_bn_apply(const float* y, const double* sums, const float* gamma, const float* beta, float* running_mean,
-                   float* running_var, float momentum, float eps, float* saved, const float* residual, float* z, long long rows,
-                   int C, int groups, int flags, void* stream);
+                   float* running_var, float momentum, float eps, float* saved, const float* residual, float* z, float* z_lo,
+                   long long rows, int C, int groups, int flags, void* stream);   /* z_lo (optional): low part of z (see ScsfmConv.in_lo) */
 /* backward: given dz (gradient of z), z, y -> dy (overwrites `dy`), dres (= dz masked by relu; may be NULL or
  * alias dz), dgamma/dbeta accumulated into. `work` holds groups*C*2 doubles. */
 int scsfm_bn_backward(const float* dz, const float* z, const float* y, const float* saved, const float* gamma,
-                      float* dy, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
-                      int relu, double* work, void* stream);
+                      float* dy, float* dy_lo, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
+                      int relu, double* work, void* stream);   /* dy_lo (optional): low part of dy (see ScsfmConv.dout_lo) */
 
 /* MaxPool2d(3, 2, 1) (resnet_encoder.py:93): idx stores the argmax tap (0..8) per output element. */
 int scsfm_maxpool_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* idx, void* stream);

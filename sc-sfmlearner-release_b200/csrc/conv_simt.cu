@@ -422,7 +422,28 @@ conv_wgrad_simt_kernel(ScsfmConv p, int k_per_split) {
     }
 }
 
-// per-channel sum of dout (bias gradient), accumulated into dbias
+// per-channel sum of dout (bias gradient), accumulated into dbias.  dout is streamed as float4; the grid stride is a multiple of
+// the float4 groups per row, so a thread always owns the same four channels: register accumulation, one shared-memory
+// reduction per block, one red.add per (block, channel).  C % 4 == 0 and C / 4 a power of two <= 64 (else the scalar variant).
+__global__ void __launch_bounds__(CT)
+bias_grad_vec_kernel(const float* __restrict__ dout, long long nvec, int gpr, float* __restrict__ dbias) {
+    __shared__ float4 s[CT];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(dout);
+    for (long long i = blockIdx.x * (long long)CT + threadIdx.x; i < nvec; i += (long long)gridDim.x * CT) {
+        const float4 v = __ldg(src + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < gpr) {              // thread t owns channel group t % gpr (CT % gpr == 0)
+        float4 t = s[threadIdx.x];
+        for (int j = threadIdx.x + gpr; j < CT; j += gpr) { t.x += s[j].x; t.y += s[j].y; t.z += s[j].z; t.w += s[j].w; }
+        float* d = dbias + 4 * threadIdx.x;
+        red_add(d, t.x); red_add(d + 1, t.y); red_add(d + 2, t.z); red_add(d + 3, t.w);
+    }
+}
+
 __global__ void __launch_bounds__(CT)
 bias_grad_kernel(const float* __restrict__ dout, int rows, int C, float* __restrict__ dbias, int rows_per_cta) {
     // thread layout: tid % cpad -> channel, tid / cpad -> row lane
@@ -443,6 +464,16 @@ bias_grad_kernel(const float* __restrict__ dout, int rows, int C, float* __restr
 
 // host-side launcher shared with the tensor-core weight gradient (conv_tc.cu)
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st) {
+    const int gpr = C / 4;
+    if ((C & 3) == 0 && gpr <= 64 && (gpr & (gpr - 1)) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
+        const long long nvec = (long long)rows * gpr;
+        long long ctas = (nvec + 8 * CT - 1) / (8 * CT);          // >= 8 float4 per thread
+        if (ctas > 148 * 8) ctas = 148 * 8;
+        if (ctas < 1) ctas = 1;
+        bias_grad_vec_kernel<<<(int)ctas, CT, 0, st>>>(dout, nvec, gpr, dbias);
+        SCSFM_CHECK_LAUNCH();
+        return SCSFM_OK;
+    }
     int ctas = (rows + 2047) / 2048;
     if (ctas > 592) ctas = 592;
     const int rpc = (rows + ctas - 1) / ctas;

@@ -43,6 +43,10 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
     const int KB = (K + TBK - 1) / TBK;
     // split-accumulate passes over the whole K range (ScsfmConv.in_lo / w_lo): raw x raw, lo(in) x raw(w), raw(in) x lo(w)
     const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.w_lo != nullptr ? 1 : 0);
+    // round-robin accumulators only in split mode (plain TF32 is bounded by its operand rounding: one accumulator, fewer TMEM
+    // columns, more resident CTAs)
+    const int nacc_rt = npass > 1 ? Cfg::NACC : 1;
+    const uint32_t tmem_cols = (uint32_t)(nacc_rt * Cfg::ACC_COLS);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -54,7 +58,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         tc::tma_prefetch_desc(&wmap);
         if (p.w_lo != nullptr) tc::tma_prefetch_desc(&wmap_lo);
     }
-    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, tmem_cols);
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
@@ -174,7 +178,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
         }
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
         constexpr int CW = BN < 32 ? BN : 32;
-        const int nacc = min(Cfg::NACC, KB * npass);            // accumulators that received at least one k-block
+        const int nacc = min(nacc_rt, KB * npass);              // accumulators that received at least one k-block
 #pragma unroll 1
         for (int cc = half; cc < BN / CW; cc += FW_PWARPS / 4) {
             uint32_t r[32];
@@ -271,7 +275,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                 for (int j = 0; j < TBK / 8; ++j) {
                     const uint64_t da = tc::make_smem_desc(a_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
                     const uint64_t db = tc::make_smem_desc(b_addr + j * 32, 16, 1024, tc::LAYOUT_SW128);
-                    tc::mma_tf32(tmem_base + (uint32_t)((kb % Cfg::NACC) * Cfg::ACC_COLS), da, db, idesc, (kb >= Cfg::NACC || j != 0) ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + (uint32_t)((kb % nacc_rt) * Cfg::ACC_COLS), da, db, idesc, (kb >= nacc_rt || j != 0) ? 1u : 0u);
                 }
                 tc::mma_commit(bar_empty + s);           // frees the stage once these MMAs have read it
             }
@@ -282,7 +286,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
 
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // w [Co][kh][kw][Ci] -> wt [Ci][jh][jw][Co] with wt[c][jy][jx][o] = w[o][dy_max - step*jy][dx_max - step*jx][c]:
@@ -351,6 +355,8 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     if (KB <= 0) return;
     // split-accumulate passes over the CTA's pixel range (ScsfmConv.in_lo / dout_lo): raw x raw, lo(in) x raw(dout), raw(in) x lo(dout)
     const int npass = STACK ? 2 : 1 + (p.in_lo != nullptr ? 1 : 0) + (p.dout_lo != nullptr ? 1 : 0);
+    const int nacc_rt = npass > 1 ? Cfg::NACC : 1;            // round-robin accumulators only in split mode
+    const uint32_t tmem_cols = (uint32_t)(nacc_rt * Cfg::ACC_COLS);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -360,7 +366,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         tc::mbar_init(bar_acc, 1);
         tc::fence_barrier_init();
     }
-    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_alloc(tmem_slot, tmem_cols);
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
@@ -467,7 +473,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
         tc::fence_after_thread_sync();
         const int quarter = warp & 3, half = warp >> 2;
         const int row = m0 + quarter * 32 + lane;
-        const int nacc = min(Cfg::NACC, KB * npass);
+        const int nacc = min(nacc_rt, KB * npass);
 #pragma unroll 1
         for (int cc = half; cc < BN / 32; cc += FW_PWARPS / 4) {
             uint32_t r[32];
@@ -507,7 +513,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
                     // LBO = 512 B between 32-channel atoms, SBO = distance between 4-pixel groups; 2 groups per MMA
                     const uint64_t da = tc::make_smem_desc(a_addr + j * (2 * 4 * 512), 512, 4 * 512, tc::LAYOUT_SW128_BASE32B);
                     const uint64_t db = tc::make_smem_desc(b_addr + j * (2 * (BN / 32) * 512), 512, (BN / 32) * 512, tc::LAYOUT_SW128_BASE32B);
-                    tc::mma_tf32(tmem_base + (uint32_t)((kb % Cfg::NACC) * Cfg::ACC_COLS), da, db, idesc, (kb >= Cfg::NACC || j != 0) ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + (uint32_t)((kb % nacc_rt) * Cfg::ACC_COLS), da, db, idesc, (kb >= nacc_rt || j != 0) ? 1u : 0u);
                 }
                 tc::mma_commit(bar_empty + s);
             }
@@ -517,7 +523,7 @@ conv_wgrad_tc_kernel(ScsfmConv p, int pix_per_split) {
     }
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == FW_PWARPS) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t rank, void* gaddr, const cuuint64_t* gdim,

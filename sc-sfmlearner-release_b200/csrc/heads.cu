@@ -7,40 +7,49 @@ namespace scsfm {
 
 constexpr int HT = 256;
 
-// out[p] = act(bias + sum_{tap,c} in[refl(p + tap)][c] * w[tap][c]);  one thread per pixel
+// out[p] = act(bias + sum_{tap,c} in[refl(p + tap)][c] * w[tap][c]).
+// TPP = C/4 threads per pixel, one float4 channel group each: a warp reads 32 consecutive float4 = 512 contiguous bytes per
+// tap (one thread per pixel made every LDG.128 touch 16 cache lines: 4x the L1 wavefronts), then a shuffle tree adds the
+// channel groups of a pixel.
+template <int TPP>
 __global__ void __launch_bounds__(HT)
 head_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                int B, int H, int W, int C, int act) {
-    extern __shared__ float sw[];        // [9][C]
-    for (int i = threadIdx.x; i < 9 * C; i += HT) sw[i] = w[i];
+                int B, int H, int W, int act) {
+    constexpr int C = 4 * TPP;
+    __shared__ float4 sw[9 * TPP];        // [9][C]
+    for (int i = threadIdx.x; i < 9 * TPP; i += HT) sw[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
     __syncthreads();
     const long long total = (long long)B * H * W;
-    const int C4 = C >> 2;
-    for (long long p = blockIdx.x * (long long)HT + threadIdx.x; p < total; p += (long long)gridDim.x * HT) {
-        const int x = (int)(p % W);
-        const long long t = p / W;
+    const int c4 = threadIdx.x % TPP;
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    constexpr int PPB = HT / TPP;         // pixels per block and iteration
+    for (long long p0 = blockIdx.x * (long long)PPB; p0 < total; p0 += (long long)gridDim.x * PPB) {
+        const long long p = p0 + threadIdx.x / TPP;
+        const bool ok = p < total;
+        const long long pc = ok ? p : total - 1;
+        const int x = (int)(pc % W);
+        const long long t = pc / W;
         const int y = (int)(t % H), b = (int)(t / H);
-        // four independent accumulation chains (one per float4 component): a single chain of 9*C dependent FMAs is
-        // latency-bound at ~4 cycles each
-        float4 acc4 = make_float4(bias ? __ldg(bias) : 0.f, 0.f, 0.f, 0.f);
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
             const int yy = reflect_index(y + dy, H);
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 const int xx = reflect_index(x + dx, W);
-                const float4* src = reinterpret_cast<const float4*>(in + (((size_t)b * H + yy) * W + xx) * C);
-                const float4* ws = reinterpret_cast<const float4*>(sw + ((dy + 1) * 3 + dx + 1) * C);
-#pragma unroll 4
-                for (int c = 0; c < C4; ++c) {
-                    const float4 a = __ldg(src + c), k = ws[c];
-                    acc4.x = fmaf(a.x, k.x, acc4.x); acc4.y = fmaf(a.y, k.y, acc4.y); acc4.z = fmaf(a.z, k.z, acc4.z); acc4.w = fmaf(a.w, k.w, acc4.w);
-                }
+                const float4 a = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + yy) * W + xx) * C) + c4);
+                const float4 k = sw[((dy + 1) * 3 + dx + 1) * TPP + c4];
+                acc4.x = fmaf(a.x, k.x, acc4.x); acc4.y = fmaf(a.y, k.y, acc4.y); acc4.z = fmaf(a.z, k.z, acc4.z); acc4.w = fmaf(a.w, k.w, acc4.w);
             }
         }
         float acc = (acc4.x + acc4.y) + (acc4.z + acc4.w);
-        if ((act & 0xff) == ACT_DISP) acc = 10.0f * (1.0f / (1.0f + expf(-acc))) + 0.01f;
-        out[p] = acc;
+#pragma unroll
+        for (int o = TPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (c4 == 0 && ok) {
+            acc += b0;
+            if ((act & 0xff) == ACT_DISP) acc = 10.0f * (1.0f / (1.0f + expf(-acc))) + 0.01f;
+            out[p] = acc;
+        }
     }
 }
 
@@ -145,11 +154,21 @@ using namespace scsfm;
 
 extern "C" int scsfm_head_conv_fwd(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int act,
                                    void* stream) {
-    SCSFM_CHECK_ARG(in && w && out && B > 0 && H >= 2 && W >= 2 && C >= 4 && (C & 3) == 0 && C <= 1024, "head_conv_fwd: bad arguments");
+    SCSFM_CHECK_ARG(in && w && out && B > 0 && H >= 2 && W >= 2, "head_conv_fwd: bad arguments");
+    SCSFM_CHECK_ARG(C == 4 || C == 8 || C == 16 || C == 32 || C == 64 || C == 128, "head_conv_fwd: C must be 4, 8, 16, 32, 64 or 128 (got %d)", C);
     const long long total = (long long)B * H * W;
-    long long g = (total + HT - 1) / HT;
+    const int ppb = HT / (C / 4);
+    long long g = (total + ppb - 1) / ppb;
     if (g > 148 * 16) g = 148 * 16;
-    head_fwd_kernel<<<(int)g, HT, 9 * C * sizeof(float), (cudaStream_t)stream>>>(in, w, bias, out, B, H, W, C, act);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C / 4) {
+        case 1: head_fwd_kernel<1><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+        case 2: head_fwd_kernel<2><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+        case 4: head_fwd_kernel<4><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+        case 8: head_fwd_kernel<8><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+        case 16: head_fwd_kernel<16><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+        default: head_fwd_kernel<32><<<(int)g, HT, 0, st>>>(in, w, bias, out, B, H, W, act); break;
+    }
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }

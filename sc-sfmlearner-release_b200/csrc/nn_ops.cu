@@ -134,7 +134,7 @@ __global__ void bn_prepare_kernel(const double* __restrict__ sums, int G, int C,
 __global__ void __launch_bounds__(NT)
 bn_apply_kernel(const float* __restrict__ y, const double* __restrict__ sums, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
-                int training, float* __restrict__ saved, const float* __restrict__ res, float* __restrict__ z,
+                int training, float* __restrict__ saved, const float* __restrict__ res, float* __restrict__ z, float* __restrict__ z_lo,
                 long long rows_per_group, int C, int G, int flags, int rows_per_cta) {
     const int g = blockIdx.y;
     const int slab4 = min(C >> 2, NT);
@@ -217,6 +217,8 @@ bn_apply_kernel(const float* __restrict__ y, const double* __restrict__ sums, co
             if (rnd) o[j] = tf32_round(o[j]);
         }
         *reinterpret_cast<float4*>(z + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        // split-accumulate mode: the low part of the tensor-core operand, produced with the tensor itself
+        if (z_lo) *reinterpret_cast<float4*>(z_lo + r * C + c) = make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3]));
     }
 }
 
@@ -286,7 +288,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
 // pass 2: dy = gamma*invstd*(dz' - mean(dz') - xhat*mean(dz' xhat)); dres = dz'.  Same grid / thread layout as pass 1.
 __global__ void __launch_bounds__(NT)
 bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
-                    const float* __restrict__ saved, const double* __restrict__ work, float* __restrict__ dy,
+                    const float* __restrict__ saved, const double* __restrict__ work, float* __restrict__ dy, float* __restrict__ dy_lo,
                     float* __restrict__ dres, long long rows_per_group, int C, int relu, int rows_per_cta) {
     const int g = blockIdx.y;
     const int slab4 = min(C >> 2, NT);
@@ -327,6 +329,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, c
         }
         if (dres) *reinterpret_cast<float4*>(dres + r * C + c) = make_float4(d[0], d[1], d[2], d[3]);
         *reinterpret_cast<float4*>(dy + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dy_lo) *reinterpret_cast<float4*>(dy_lo + r * C + c) = make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3]));
     }
 }
 
@@ -659,20 +662,20 @@ static void bn_grid(long long rpg, int C, int groups, dim3& grid, int& rpc) {
 // eval (sums == NULL): running statistics.
 extern "C" int scsfm_bn_apply(const float* y, const double* sums, const float* gamma, const float* beta, float* running_mean,
                               float* running_var, float momentum, float eps, float* saved, const float* residual, float* z,
-                              long long rows, int C, int groups, int flags, void* stream) {
+                              float* z_lo, long long rows, int C, int groups, int flags, void* stream) {
     SCSFM_CHECK_ARG(y && gamma && beta && running_mean && running_var && saved && z && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 &&
                         rows % groups == 0, "bn_apply: bad arguments");
     dim3 grid;
     int rpc;
     bn_grid(rows / groups, C, groups, grid, rpc);
-    bn_apply_kernel<<<grid, NT, 0, ST>>>(y, sums, gamma, beta, running_mean, running_var, momentum, eps, sums != nullptr, saved, residual, z,
+    bn_apply_kernel<<<grid, NT, 0, ST>>>(y, sums, gamma, beta, running_mean, running_var, momentum, eps, sums != nullptr, saved, residual, z, z_lo,
                                          rows / groups, C, groups, flags, rpc);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
 
 extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y, const float* saved, const float* gamma,
-                                 float* dy, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
+                                 float* dy, float* dy_lo, float* dres, float* dgamma, float* dbeta, long long rows, int C, int groups,
                                  int relu, double* work, void* stream) {
     (void)gamma;
     SCSFM_CHECK_ARG(dz && y && saved && dy && work && rows > 0 && C > 0 && (C & 3) == 0 && groups > 0 && rows % groups == 0,
@@ -695,7 +698,7 @@ extern "C" int scsfm_bn_backward(const float* dz, const float* z, const float* y
         dim3 grid2;
         int rpc2;
         bn_grid(rpg, C, groups, grid2, rpc2);
-        bn_bwd_apply_kernel<<<grid2, NT, 0, ST>>>(dz, z, y, saved, work, dy, dres, rpg, C, relu, rpc2);
+        bn_bwd_apply_kernel<<<grid2, NT, 0, ST>>>(dz, z, y, saved, work, dy, dy_lo, dres, rpg, C, relu, rpc2);
     }
     SCSFM_CHECK_LAUNCH();
     if (dgamma || dbeta) {

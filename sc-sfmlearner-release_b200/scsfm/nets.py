@@ -401,7 +401,7 @@ def _bn_fwd(cx, y, sums, bn, training, relu, residual, groups):
     running-stat updates, stay per call exactly as in train.py:427-442).  num_batches_tracked of every layer is bumped
     by one add per network call (ArenaNet._nbt, see encoder_forward)."""
     return O.bn_apply(y, sums if training else None, bn.weight, bn.bias, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
-                      residual, (1 if relu else 0) | cx.rnd(), groups)
+                      residual, (1 if relu else 0) | cx.rnd(), groups, cx.split)
 
 
 def _conv_bn(cx, x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
@@ -414,7 +414,7 @@ def _conv_bn(cx, x, conv, bn, stride, pad, training, relu, residual=None, groups
 
 def _conv_bn_bwd(cx, dz, z, y, saved, x, conv, bn, stride, pad, relu, want_dres, need_dx, addend=None, groups=1):
     """Backward through relu?(bn(conv(x)) [+res]).  Returns (dx or None, dres or None)."""
-    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, (1 if relu else 0) | cx.rnd(), want_dres, groups)
+    dy, dres = O.bn_backward(dz, z, y, saved, bn.weight.grad, bn.bias.grad, (1 if relu else 0) | cx.rnd(), want_dres, groups, cx.split)
     cx.conv_wgrad(x, dy, ArenaNet.g(conv.weight), None, stride, pad, O.PAD_ZERO)
     dx = cx.conv_dgrad(dy, conv.w_op(cx), x.shape, stride, pad, addend) if need_dx else None
     return dx, dres
@@ -533,7 +533,7 @@ def encoder_backward(cx, enc, rec, d_feats):
     x = rec["x"]
     if x.shape[-1] != t.conv1.weight.shape[1]:
         # padded-channel stem (tf32 mode): weight gradient in the padded layout, then folded into the gradient arena
-        dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | cx.rnd(), False, rec["G"])
+        dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | cx.rnd(), False, rec["G"], cx.split)
         dw = torch.zeros(t.conv1.weight.shape[0], t.conv1.k, t.conv1.k, x.shape[-1], device=x.device, dtype=torch.float32)
         cx.conv_wgrad(x, dy, dw, None, 2, 3, O.PAD_ZERO)
         O.unpad_add_(ArenaNet.g(t.conv1.weight), dw)

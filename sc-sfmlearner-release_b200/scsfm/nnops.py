@@ -68,8 +68,8 @@ def _lib():
         lib.scsfm_pad_channels.argtypes = [P, LL, I, I, P, I, P]
         lib.scsfm_unpad_add.argtypes = [P, LL, I, I, P, P]
         lib.scsfm_bn_prepare.argtypes = [P, I, I, LL, P, P, P, P, F, F, I, P, P]
-        lib.scsfm_bn_apply.argtypes = [P, P, P, P, P, P, F, F, P, P, P, LL, I, I, I, P]
-        lib.scsfm_bn_backward.argtypes = [P, P, P, P, P, P, P, P, P, LL, I, I, I, P, P]
+        lib.scsfm_bn_apply.argtypes = [P, P, P, P, P, P, F, F, P, P, P, P, LL, I, I, I, P]
+        lib.scsfm_bn_backward.argtypes = [P, P, P, P, P, P, P, P, P, P, LL, I, I, I, P, P]
         lib.scsfm_maxpool_fwd.argtypes = [P, I, I, I, I, P, P, P]
         lib.scsfm_maxpool_bwd.argtypes = [P, P, I, I, I, I, P, I, P]
         lib.scsfm_upcat_fwd.argtypes = [P, P, I, I, I, I, I, P, P]
@@ -382,28 +382,36 @@ def bn_prepare(sums, groups, count, gamma, beta, rmean, rvar, momentum, eps, tra
     return saved
 
 
-def bn_apply(y, sums, gamma, beta, rmean, rvar, momentum, eps, residual, flags, groups=1):
+def bn_apply(y, sums, gamma, beta, rmean, rvar, momentum, eps, residual, flags, groups=1, with_lo=False):
     """z = relu?(bn(y) + residual); statistics from the fused sums (training) or the running stats (sums=None).
-    Returns (z, saved) with saved[g][c] = {scale, shift, mean, invstd} for the backward."""
+    Returns (z, saved) with saved[g][c] = {scale, shift, mean, invstd} for the backward.  with_lo: also produce lo(z), the
+    low part the split-accumulate convolutions read (attached to z like lo_of() would)."""
     z = torch.empty_like(y)
+    z_lo = torch.empty_like(y) if with_lo else None
     C = y.shape[-1]
     saved = empty((groups, C, 4), y)
     rows = y.numel() // C
     L.launch(_lib().scsfm_bn_apply, "scsfm_bn_apply", "bn_apply", 1, (12.0 if residual is not None else 8.0) * y.numel(), L.ptr(y), L.ptr(sums),
-             L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar), momentum, eps, L.ptr(saved), L.ptr(residual), L.ptr(z), rows, C, groups,
-             int(flags), L.stream())
+             L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar), momentum, eps, L.ptr(saved), L.ptr(residual), L.ptr(z), L.ptr(z_lo), rows, C,
+             groups, int(flags), L.stream())
+    if with_lo:
+        z._scsfm_lo = z_lo
     return z, saved
 
 
-def bn_backward(dz, z, y, saved, dgamma, dbeta, relu, want_dres, groups=1):
-    """Returns (dy, dres).  dres (= dz gated by the ReLU) is written in place over dz when requested."""
+def bn_backward(dz, z, y, saved, dgamma, dbeta, relu, want_dres, groups=1, with_lo=False):
+    """Returns (dy, dres).  dres (= dz gated by the ReLU) is written in place over dz when requested.  with_lo: also
+    produce lo(dy) (attached to dy like lo_of() would)."""
     C = y.shape[-1]
     rows = y.numel() // C
     dy = torch.empty_like(y)
+    dy_lo = torch.empty_like(y) if with_lo else None
     work = torch.empty(groups * C * 2, device=y.device, dtype=torch.float64)
     dres = dz if want_dres else None
-    L.launch(_lib().scsfm_bn_backward, "scsfm_bn_backward", "bn_bwd", 4, 28.0 * y.numel(), L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(saved), None, L.ptr(dy), L.ptr(dres), L.ptr(dgamma),
-                                     L.ptr(dbeta), rows, C, groups, int(relu), L.ptr(work), L.stream())
+    L.launch(_lib().scsfm_bn_backward, "scsfm_bn_backward", "bn_bwd", 4, 28.0 * y.numel(), L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(saved), None, L.ptr(dy),
+             L.ptr(dy_lo), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), rows, C, groups, int(relu), L.ptr(work), L.stream())
+    if with_lo:
+        dy._scsfm_lo = dy_lo
     return dy, dres
 
 

@@ -110,12 +110,16 @@ def test_bn_pool_upcat_ops_vs_torch():
     sums[3] = torch.stack([yc.double().sum((0, 1, 2)), (yc.double() ** 2).sum((0, 1, 2))], 1)
     gm, bt = gamma.detach().float().to(DEV), beta.detach().float().to(DEV)
     rmc, rvc = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    zc, saved = O.bn_apply(yc, sums, gm, bt, rmc, rvc, 0.1, 1e-5, rc, 1)
+    zc, saved = O.bn_apply(yc, sums, gm, bt, rmc, rvc, 0.1, 1e-5, rc, 1, 1, True)
     assert rel_l2(zc.permute(0, 3, 1, 2), z.detach()) < 2e-6
+    assert torch.equal(zc._scsfm_lo, O.split_tf32(zc))           # low part produced with the tensor itself (split-accumulate mode)
+    hi = (zc.view(torch.int32) & -8192).view(torch.float32)      # what kind::tf32 reads: the upper 19 bits
+    assert float((hi.double() + zc._scsfm_lo.double() - zc.double()).abs().max()) <= 2.0 ** -20 * float(zc.abs().max())
     assert rel_l2(rmc, rm) < 1e-5 and rel_l2(rvc, rv) < 1e-5
     dgm, dbt = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dzc = nh(dz)
-    dy, dres = O.bn_backward(dzc, zc, yc, saved, dgm, dbt, True, True)
+    dy, dres = O.bn_backward(dzc, zc, yc, saved, dgm, dbt, True, True, 1, True)
+    assert torch.equal(dy._scsfm_lo, O.split_tf32(dy))
     assert rel_l2(dy.permute(0, 3, 1, 2), y.grad) < 1e-5
     assert rel_l2(dres.permute(0, 3, 1, 2), res.grad) < 1e-6
     assert rel_l2(dgm, gamma.grad) < 1e-5 and rel_l2(dbt, beta.grad) < 1e-5
