@@ -219,7 +219,9 @@ class ArenaNet(nn.Module):
         """"fp32" (exact CUDA-core kernels), "tf32" (tcgen05, single TF32 product) or "tf32x3" (tcgen05 with
         split-accumulate operands: fp32-level products, the parity mode on the tensor cores).  Returns self."""
         if mode != self.ctx.mode:
+            pool = self.ctx.sums_pool
             self.ctx = O.ConvCtx(mode)
+            self.ctx.sums_pool = pool
             self._tf32_version = None          # the operand mirror holds something else in every mode
         return self
 
@@ -393,7 +395,12 @@ class _SumsPool:
         return buf[start:start + n]
 
 
-_SUMS = _SumsPool()
+def _pool(cx):
+    """The BatchNorm-sums pool of one network (lives on its ConvCtx: two networks may run concurrently on two streams, and
+    a pool is sized by its own network's calls during the eager warm-up, i.e. before any CUDA-graph capture)."""
+    if cx.sums_pool is None:
+        cx.sums_pool = _SumsPool()
+    return cx.sums_pool
 
 
 def _bn_fwd(cx, y, sums, bn, training, relu, residual, groups):
@@ -406,7 +413,7 @@ def _bn_fwd(cx, y, sums, bn, training, relu, residual, groups):
 
 def _conv_bn(cx, x, conv, bn, stride, pad, training, relu, residual=None, groups=1):
     C = conv.weight.shape[0]
-    sums = _SUMS.take(O.BN_SLOTS * groups * C * 2, x.device) if training else None
+    sums = _pool(cx).take(O.BN_SLOTS * groups * C * 2, x.device) if training else None
     y = cx.conv_fwd(x, conv.w_op(cx), None, stride, pad, O.PAD_ZERO, O.ACT_NONE, sums, groups, conv.w_lo(cx))
     z, saved = _bn_fwd(cx, y, sums, bn, training, relu, residual, groups)
     return y, z, saved
@@ -435,7 +442,7 @@ def block_forward(cx, blk, x, training, G=1):
     if blk.downsample is not None:
         r["yd"], sc, r["sd"] = _conv_bn(cx, x, blk.downsample[0], blk.downsample[1], blk.stride, 0, training, False, None, G)
     C = last_conv.weight.shape[0]
-    sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x.device) if training else None
+    sums = _pool(cx).take(O.BN_SLOTS * G * C * 2, x.device) if training else None
     y = cx.conv_fwd(last_in, last_conv.w_op(cx), None, ls, lp, O.PAD_ZERO, O.ACT_NONE, sums, G, last_conv.w_lo(cx))
     out, saved = _bn_fwd(cx, y, sums, last_bn, training, True, sc, G)
     r["y" + key], r["s" + key], r["out"] = y, saved, out
@@ -471,7 +478,7 @@ def encoder_forward(cx, enc, imgs, training, G=1):
     t = enc.encoder
     rec = {"G": G}
     if training:
-        _SUMS.begin(imgs[0].device)
+        _pool(cx).begin(imgs[0].device)
         nbt = getattr(enc, "_nbt", None)
         if nbt is not None:
             nbt.add_(G)                      # every BatchNorm layer's num_batches_tracked (views of this tensor)
@@ -486,7 +493,7 @@ def encoder_forward(cx, enc, imgs, training, G=1):
         w0 = O.pad_channels(t.conv1.w_khwc(), cpad, cx.operand)
         w0_lo = O.pad_channels(t.conv1.w_khwc(), cpad, O.OPERAND_LO) if cx.split else None
         C = w0.shape[0]
-        sums = _SUMS.take(O.BN_SLOTS * G * C * 2, x_nhwc.device) if training else None
+        sums = _pool(cx).take(O.BN_SLOTS * G * C * 2, x_nhwc.device) if training else None
         rec["y0"] = cx.conv_fwd(x_nhwc, w0, None, 2, 3, O.PAD_ZERO, O.ACT_NONE, sums, G, w0_lo)
         f0, rec["s0"] = _bn_fwd(cx, rec["y0"], sums, t.bn1, training, True, None, G)
     else:

@@ -188,6 +188,7 @@ class ConvCtx:
         self.debug = None             # ScsfmConv.debug: uint64 tensor [8 * SMs] of per-role cycle counters, or None
         self._flips = {}              # (source pointer, shape, stride, pad, operand) -> (source tensor, flipped weights)
         self._table = None
+        self.sums_pool = None         # fp64 scratch of the fused BatchNorm sums of this network's calls (scsfm.nets._pool)
 
     # -- mode -----------------------------------------------------------------------------------------
     @property

@@ -34,7 +34,7 @@ class Trainer:
 
     def __init__(self, disp_net, pose_net, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.0, num_scales=1, with_ssim=1,
                  with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None, conv_mode=None,
-                 exact_global_masks=False):
+                 exact_global_masks=False, overlap_nets=False):
         self.disp_net, self.pose_net = disp_net, pose_net
         if conv_mode is not None:           # "fp32" | "tf32" | "tf32x3" (nnops.MODES); None keeps each network's own setting
             disp_net.set_conv_mode(conv_mode)
@@ -54,6 +54,8 @@ class Trainer:
         # 10000-pixel thresholds and therefore the gradients are those of the GLOBAL batch -- exactly what the reference's
         # nn.DataParallel computes on the gathered outputs (per-GPU BatchNorm, global loss; train.py:168-169).
         self.exact_global_masks = bool(exact_global_masks)
+        self.overlap_nets = bool(overlap_nets)
+        self._side = None
         self._graph = None
         self.launches_per_step = None
         if self.distributed:
@@ -66,8 +68,25 @@ class Trainer:
             self.exchange.broadcast_params([disp_net.flat_params(), pose_net.flat_params()])   # identical replicas
 
     def losses(self, tgt_img, ref_imgs, intrinsics):
-        tgt_depth, ref_depths = compute_depth(self.disp_net, tgt_img, ref_imgs)
-        poses, poses_inv = compute_pose_with_inv(self.pose_net, tgt_img, ref_imgs)
+        if self.overlap_nets:
+            # the two networks are independent until the losses: PoseResNet runs on a side stream next to DispResNet (autograd
+            # replays each network's backward on the stream of its forward).  Their big layers fill the GPU on their own; the
+            # gain is in the deep 8x26 / 16x52 layers, whose 40..100 CTAs leave a third of the SMs idle.  Fork / join through
+            # events (capturable in a CUDA graph); tensors made on the side stream are first used on the main stream after
+            # the join and released only after the whole step has been enqueued.
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(fork)
+                poses, poses_inv = compute_pose_with_inv(self.pose_net, tgt_img, ref_imgs)
+            tgt_depth, ref_depths = compute_depth(self.disp_net, tgt_img, ref_imgs)
+            main.wait_stream(self._side)
+        else:
+            tgt_depth, ref_depths = compute_depth(self.disp_net, tgt_img, ref_imgs)
+            poses, poses_inv = compute_pose_with_inv(self.pose_net, tgt_img, ref_imgs)
         c = self.cfg
         if self.exchange is not None and self.exact_global_masks:
             from . import loss_ops

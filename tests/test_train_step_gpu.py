@@ -261,3 +261,34 @@ def test_tf32_operand_mirror_and_batched_flips_stay_exact(mode):
         with torch.no_grad():
             next(iter(gr.disp_net.parameters())).mul_(1.5)
         assert gr.disp_net._tf32_version != gr.disp_net._versions()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_overlapped_networks_reproduce_the_serial_step(graph):
+    """Trainer(overlap_nets=True): PoseResNet on a side stream next to DispResNet (forward and, through autograd's stream
+    tracking, backward).  Same kernels on the same data: losses, gradients and updated parameters must match the serial step to
+    atomics-order noise, eagerly and as a captured CUDA graph (fork / join inside the graph)."""
+    import models
+    from scsfm import synth
+    from scsfm.trainer import Trainer
+    tgt, refs, K = synth.triplet(9, 2, 128, 160)
+    args = (tgt.to(DEV), [r.to(DEV) for r in refs], K.to(DEV))
+
+    def make(overlap):
+        d, p = models.DispResNet(18, False), models.PoseResNet(18, False)
+        d.load_state_dict(det_weights(d.state_dict())); p.load_state_dict(det_weights(p.state_dict()))
+        return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False, conv_mode="tf32x3",
+                       overlap_nets=overlap)
+    a, b = make(False), make(True)
+    if graph:
+        b.capture(*args)
+    for it in range(3):
+        la = [float(v) for v in a.step(*args)]
+        lb = [float(v) for v in b.step(*args)]
+        np.testing.assert_allclose(lb, la, rtol=1e-5 if it == 0 else 5e-3, atol=1e-7)
+        if it == 0 and not graph:
+            for na, nb in ((a.disp_net, b.disp_net), (a.pose_net, b.pose_net)):
+                assert rel_l2(nb.flat_grads(), na.flat_grads()) < 1e-4
+    torch.cuda.synchronize()
+    assert float((b.disp_net.flat_params() - a.disp_net.flat_params()).abs().max()) <= 6.1e-4
+    assert float((b.pose_net.flat_params() - a.pose_net.flat_params()).abs().max()) <= 6.1e-4
