@@ -223,7 +223,7 @@ def run_ours(args):
         torch.manual_seed(0)
         disp, pose = models.DispResNet(cfg["dl"], False).to(dev).train(), models.PoseResNet(cfg["pl"], False).to(dev).train()
         return Trainer(disp, pose, lr=1e-4, num_scales=1, with_ssim=1, with_mask=1, with_auto_mask=1, padding_mode="zeros",
-                       w1=1.0, w2=0.1, w3=0.5, distributed=world > 1, conv_mode=mode, overlap_nets=bool(args.overlap_nets))
+                       w1=1.0, w2=0.1, w3=0.5, distributed=world > 1, conv_mode=mode, overlap_nets=bool(args.overlap_nets), overlap_wgrad=bool(args.overlap_wgrad))
 
     def barrier():
         if world > 1:
@@ -387,7 +387,7 @@ def run_ours(args):
         "data": "synthetic", "impl": "ours",
         "config": {"workload": cfg["label"], "name": args.config, "global_batch": B * world, "height": cfg["H"], "width": cfg["W"],
                    "n_ref": cfg["n_ref"], "parallelism": "dp%d" % world, "conv_mode": args.conv_mode,
-                   "l2": "flushed (256 MiB write) before every step", "cuda_graph": graphed, "overlap_nets": bool(args.overlap_nets),
+                   "l2": "flushed (256 MiB write) before every step", "cuda_graph": graphed, "overlap_nets": bool(args.overlap_nets), "overlap_wgrad": bool(args.overlap_wgrad),
                    "eager_ms_per_step": round(ms_eager / args.steps, 3), "loss_flags": "num_scales=1 ssim=1 mask=1 auto_mask=1 zeros"},
         "e2e": {"value": round(frames / (ms_e2e * 1e-3), 3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16, "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -473,6 +473,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-tf32-extra", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--overlap-wgrad", type=int, default=0, help="1: weight gradients on a side stream per network (Trainer(overlap_wgrad=True))")
     ap.add_argument("--overlap-nets", type=int, default=0, help="1: PoseResNet on a side stream next to DispResNet (Trainer(overlap_nets=True))")
     args = ap.parse_args()
     if args.impl == "reference":

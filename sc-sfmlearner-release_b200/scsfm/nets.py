@@ -219,9 +219,9 @@ class ArenaNet(nn.Module):
         """"fp32" (exact CUDA-core kernels), "tf32" (tcgen05, single TF32 product) or "tf32x3" (tcgen05 with
         split-accumulate operands: fp32-level products, the parity mode on the tensor cores).  Returns self."""
         if mode != self.ctx.mode:
-            pool = self.ctx.sums_pool
+            pool, ws = self.ctx.sums_pool, self.ctx.wgrad_stream
             self.ctx = O.ConvCtx(mode)
-            self.ctx.sums_pool = pool
+            self.ctx.sums_pool, self.ctx.wgrad_stream = pool, ws
             self._tf32_version = None          # the operand mirror holds something else in every mode
         return self
 
@@ -358,6 +358,7 @@ class _NetCall(torch.autograd.Function):
         net = ctx.net
         net._attach_grads()
         net._backward_impl(ctx.rec, [None if g is None else g.contiguous() for g in grads])
+        net.ctx.join_wgrad()           # weight gradients enqueued on the side stream (if any) are part of this backward
         ctx.rec = None
         net._pending -= 1
         if net._pending == 0 and net.grads_ready_callback is not None:
@@ -543,7 +544,8 @@ def encoder_backward(cx, enc, rec, d_feats):
         dy, _ = O.bn_backward(d_f0, f0, rec["y0"], rec["s0"], t.bn1.weight.grad, t.bn1.bias.grad, 1 | cx.rnd(), False, rec["G"], cx.split)
         dw = torch.zeros(t.conv1.weight.shape[0], t.conv1.k, t.conv1.k, x.shape[-1], device=x.device, dtype=torch.float32)
         cx.conv_wgrad(x, dy, dw, None, 2, 3, O.PAD_ZERO)
-        O.unpad_add_(ArenaNet.g(t.conv1.weight), dw)
+        with cx.on_wgrad_stream([dw]):
+            O.unpad_add_(ArenaNet.g(t.conv1.weight), dw)
     else:
         _conv_bn_bwd(cx, d_f0, f0, rec["y0"], rec["s0"], x, t.conv1, t.bn1, 2, 3, True, False, False, None, rec["G"])
 

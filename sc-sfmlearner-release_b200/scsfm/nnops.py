@@ -189,6 +189,11 @@ class ConvCtx:
         self._flips = {}              # (source pointer, shape, stride, pad, operand) -> (source tensor, flipped weights)
         self._table = None
         self.sums_pool = None         # fp64 scratch of the fused BatchNorm sums of this network's calls (scsfm.nets._pool)
+        # Optional side stream for the weight gradients: a layer's wgrad is off the backward's critical path (only the
+        # optimizer reads dW), so it can run next to the dgrad / BatchNorm chain and fill the SMs their small grids leave idle.
+        # Operand tensors are kept alive until join_wgrad() so that the caching allocator cannot recycle them early.
+        self.wgrad_stream = None
+        self._wgrad_keep = []
 
     # -- mode -----------------------------------------------------------------------------------------
     @property
@@ -297,20 +302,43 @@ class ConvCtx:
         return din
 
     def conv_wgrad(self, x, dout, dw, dbias=None, stride=1, pad=0, pad_mode=PAD_ZERO):
-        """dw += dout^T * gather(x); dbias += column sums of dout."""
+        """dw += dout^T * gather(x); dbias += column sums of dout.  With a wgrad stream set the launch goes there (after
+        everything already enqueued on the current stream); join_wgrad() must follow before dw is read."""
         lib = _lib()
         d = conv_desc(x.shape, dw, stride, pad, pad_mode, ACT_NONE)
         assert (d.Ho, d.Wo, d.Cout) == tuple(dout.shape[1:])
         d.inp, d.dout, d.dw, d.dbias = x.data_ptr(), dout.data_ptr(), dw.data_ptr(), dbias.data_ptr() if dbias is not None else None
         d.w = None
         tc = self._use_tc("wgrad", d.Cin, d.Cout, d.kh, stride)
+        keep = [x, dout]
         if tc and self.split:
-            d.in_lo, d.dout_lo = lo_of(x).data_ptr(), lo_of(dout).data_ptr()
+            x_lo, dout_lo = lo_of(x), lo_of(dout)          # (computed on the CURRENT stream: the data gradient reads them too)
+            d.in_lo, d.dout_lo = x_lo.data_ptr(), dout_lo.data_ptr()
+            keep += [x_lo, dout_lo]
         self._finish(d)
         _tag(d)
         fn = lib.scsfm_conv2d_wgrad_tc if tc else lib.scsfm_conv2d_wgrad_simt
-        L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
-                 ctypes.byref(d), L.stream())
+        with self.on_wgrad_stream(keep):
+            L.launch(fn, "scsfm_conv2d_wgrad", "conv_wgrad_tc" if tc else "conv_wgrad_simt", 2 if dbias is not None else 1, _flops(d),
+                     ctypes.byref(d), L.stream())
+
+    def on_wgrad_stream(self, keep=()):
+        """Context: the weight-gradient side stream, ordered after the work already enqueued on the current stream (no-op
+        without a side stream)."""
+        import contextlib
+        if self.wgrad_stream is None:
+            return contextlib.nullcontext()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.wgrad_stream.wait_event(ev)
+        self._wgrad_keep.extend(keep)
+        return torch.cuda.stream(self.wgrad_stream)
+
+    def join_wgrad(self):
+        """The current stream waits for every weight gradient enqueued so far; their operands may be released."""
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+        self._wgrad_keep.clear()
 
 
 def head_fwd(x, w, bias, act):

@@ -263,8 +263,9 @@ def test_tf32_operand_mirror_and_batched_flips_stay_exact(mode):
         assert gr.disp_net._tf32_version != gr.disp_net._versions()
 
 
+@pytest.mark.parametrize("wgrad", [False, True])
 @pytest.mark.parametrize("graph", [False, True])
-def test_overlapped_networks_reproduce_the_serial_step(graph):
+def test_overlapped_networks_reproduce_the_serial_step(graph, wgrad):
     """Trainer(overlap_nets=True): PoseResNet on a side stream next to DispResNet (forward and, through autograd's stream
     tracking, backward).  Same kernels on the same data: losses, gradients and updated parameters must match the serial step to
     atomics-order noise, eagerly and as a captured CUDA graph (fork / join inside the graph)."""
@@ -278,7 +279,7 @@ def test_overlapped_networks_reproduce_the_serial_step(graph):
         d, p = models.DispResNet(18, False), models.PoseResNet(18, False)
         d.load_state_dict(det_weights(d.state_dict())); p.load_state_dict(det_weights(p.state_dict()))
         return Trainer(d.to(DEV).train(), p.to(DEV).train(), lr=1e-4, with_auto_mask=1, distributed=False, conv_mode="tf32x3",
-                       overlap_nets=overlap)
+                       overlap_nets=overlap, overlap_wgrad=overlap and wgrad)
     a, b = make(False), make(True)
     if graph:
         b.capture(*args)
