@@ -473,8 +473,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-tf32-extra", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
-    ap.add_argument("--overlap-wgrad", type=int, default=0, help="1: weight gradients on a side stream per network (Trainer(overlap_wgrad=True))")
-    ap.add_argument("--overlap-nets", type=int, default=0, help="1: PoseResNet on a side stream next to DispResNet (Trainer(overlap_nets=True))")
+    ap.add_argument("--overlap-wgrad", type=int, default=1, help="1 (default): weight gradients on a side stream per network (Trainer(overlap_wgrad=True))")
+    ap.add_argument("--overlap-nets", type=int, default=1, help="1 (default): PoseResNet on a side stream next to DispResNet (Trainer(overlap_nets=True))")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -34,7 +34,7 @@ class Trainer:
 
     def __init__(self, disp_net, pose_net, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.0, num_scales=1, with_ssim=1,
                  with_mask=1, with_auto_mask=0, padding_mode="zeros", w1=1.0, w2=0.1, w3=0.5, distributed=None, conv_mode=None,
-                 exact_global_masks=False, overlap_nets=False, overlap_wgrad=False):
+                 exact_global_masks=False, overlap_nets=True, overlap_wgrad=True):
         self.disp_net, self.pose_net = disp_net, pose_net
         if conv_mode is not None:           # "fp32" | "tf32" | "tf32x3" (nnops.MODES); None keeps each network's own setting
             disp_net.set_conv_mode(conv_mode)

@@ -71,6 +71,7 @@ parser.add_argument("--conv-mode", choices=["fp32", "tf32", "tf32x3"], default="
                     help="tf32x3 = tcgen05 tensor cores with split-accumulate operands (fp32-level results, the parity mode); tf32 = "
                          "tcgen05 single TF32 product (cuDNN's default arithmetic, fastest); fp32 = exact CUDA-core convolutions")
 parser.add_argument("--cuda-graph", type=int, default=1, help="capture the training step in a CUDA graph (single GPU)")
+parser.add_argument("--overlap", type=int, default=1, help="run PoseResNet next to DispResNet and the weight gradients on side streams")
 parser.add_argument("--synthetic-size", type=int, nargs=2, default=[256, 832], metavar=("H", "W"))
 
 best_error = -1
@@ -179,7 +180,7 @@ def main():
     trainer = Trainer(disp_net, pose_net, lr=args.lr, betas=(args.momentum, args.beta), weight_decay=args.weight_decay,
                       num_scales=args.num_scales, with_ssim=args.with_ssim, with_mask=args.with_mask,
                       with_auto_mask=args.with_auto_mask, padding_mode=args.padding_mode, w1=args.photo_loss_weight,
-                      w2=args.smooth_loss_weight, w3=args.geometry_consistency_weight, distributed=world > 1, conv_mode=args.conv_mode)
+                      w2=args.smooth_loss_weight, w3=args.geometry_consistency_weight, distributed=world > 1, conv_mode=args.conv_mode, overlap_nets=bool(args.overlap), overlap_wgrad=bool(args.overlap))
     if rank == 0:
         with open(os.path.join(args.save_path, args.log_summary), "w") as f:
             csv.writer(f, delimiter="\t").writerow(["train_loss", "validation_loss"])
