@@ -1,46 +1,53 @@
-// Weight gradient of a stride-1, zero-padded convolution with both operands delivered by TMA (selected per call with
-// SCSFM_TUNE_WGRAD(2); validated on B200 against the cp.async kernel and fp64, profiles/r02_wgrad_tma_check.txt).
+// Weight gradient of a stride-1, zero-padded convolution with both operands delivered by TMA (validated on B200 against
+// the cp.async kernel and fp64: profiles/r02_wgrad_tma_check.txt; default for Cout >= 64 in split mode).
 //
 //   D[o (M = 128 TMEM lanes: output channels), (dy, chunk c, ch) (N = kh * G * 32 columns)] +=
 //        sum over the pixels p of a tile   dout[p, o] * in[p + (dy, dx) - pad, 32 * (G * cg + c) + ch]
 //
-// Measured in round 1 (profiles/r01b_wgrad_wide_check.txt): the cp.async weight-gradient kernels are bound by their 256
-// producer threads, not by the MMA count.  Here one thread issues TMA loads instead:
 //  * pixels are the K dimension and both operands are "MN-major" (channels contiguous), which for 32-bit types means the
 //    UMMA layout SWIZZLE_128B_BASE32B; CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B is its TMA twin (rows of 128 B = 32 channels of
 //    one pixel, 32-byte chunks XOR-swizzled with the pixel index mod 4);
-//  * a CTA owns one (Cout tile, group of G <= 2 channel chunks, dx) slice of dW and a range of pixel tiles (TH x TW = 128
-//    pixels of one image, TW in {8, 16}); per tile it loads the dout tile (one box per 32 output channels) and the input
-//    rows y0-pad .. y0-pad+TH+kh-2 shifted by dx, laid out [row][chunk][x][32 ch], so the (dy, chunk) operand atoms of the
-//    tile row r start at ((r + dy) * G + c) * TW * 128 bytes: one uniform stride TW*128 = the descriptor's LBO.  The kh
-//    vertical taps therefore share one load, as in conv_tma.cu;
-//  * one tcgen05.mma (K = 8 pixels) per 8-pixel slice of a tile row: 16 per tile, M = 128, N = kh*G*32 <= 192;
-//  * split-K over pixel-tile ranges (gridDim.z), fp32 vector red.add of the partial dW tiles.
-// Reflection-padded layers, stride 2 and kernels larger than 3x3 stay on the cp.async kernel.
+//  * a CTA owns one (Cout tile, group of G <= 2 channel chunks, dx) slice of dW and a range of pixel tiles (TH x TW = 64
+//    pixels of one image, TW in {8, 16}); a stage holds an M part (the dout tile, one TMA box per 32 output channels) and an
+//    N part (the input rows y0-pad .. y0-pad+TH+kh-2 shifted by dx, laid out [row][chunk][x][32 ch], so the (dy, chunk)
+//    operand atoms of the tile row r start at ((r + dy) * G + c) * TW * 128 bytes: one uniform stride TW*128 = the
+//    descriptor's LBO; the kh vertical taps share one load, as in conv_tma.cu);
+//  * one tcgen05.mma (K = 8 pixels) per 8-pixel slice of a tile row: 8 per tile and pass, M = 128, N = kh*G*32 <= 192;
+//  * split mode (ScsfmConv.in_lo / dout_lo): a tile takes TWO stages and its passes share operands ACROSS them, so every
+//    operand crosses L2 -> shared memory once per tile instead of once per pass (the round-2 measurement: with one full stage
+//    per pass the kernel asked for 46 B/cycle/SM, above the chip-wide L2 cap of ~42):
+//        stage A = (dout,    lo(x))        pass 1: M = A, N = A      lo(x) . dout
+//        stage B = (lo(dout), x   )        pass 2: M = B, N = B      x . lo(dout)
+//                                          pass 3: M = A, N = B      x . dout         (the big term last)
+//    With Cout <= 64 dout sits in atoms 0-1 and lo(dout) in atoms 2-3 of stage A's M part (both red.add into dw), stage B
+//    carries only x:  pass 1: M = A, N = A;  pass 2: M = A, N = B  -- two MMAs per K8 slice instead of three;
+//  * the tensor core adds into TMEM with truncation (bias ~3e-8 per MMA of a chain): in split mode every tile is its own
+//    accumulation chain, drained by the epilogue warps into registers (round-to-nearest adds) while the MMAs of the next
+//    tile run in the second TMEM buffer; plain TF32: one chain per CTA;
+//  * split-K over pixel-tile ranges (gridDim.z, wave-aware count), fp32 vector red.add of the partial dW tiles.
+// Reflection-padded layers (beyond the zero-padded pass), stride 2 and kernels larger than 3x3 stay on the cp.async kernel.
 #include "conv_tc.cuh"
 
 namespace scsfm {
 
 constexpr int WT_EWARPS = 8;
 constexpr int WT_THREADS = (WT_EWARPS + 2) * 32;
-constexpr int WT_MAX_STAGES = 4;
-constexpr int WT_DOUT_BYTES = 4 * TBM * 128;        // four 32-channel atoms x 128 pixels x 128 B (atoms beyond Cout stay stale)
+constexpr int WT_MAX_STAGES = 6;
+constexpr int WT_PIX = 64;                           // pixels per tile
+constexpr int WT_ATOM_BYTES = WT_PIX * 128;          // one 32-channel atom of the dout tile
+constexpr int WT_M_BYTES = 4 * WT_ATOM_BYTES;        // M part of a stage: four atoms (atoms beyond the loaded ones stay stale)
 constexpr int WT_SMEM_MAX = 232448;
 
 struct WtGeom {
-    int tw_log2;                 // TW = 1 << tw_log2 (3 or 4), TH = 128 >> tw_log2
+    int tw_log2;                 // TW = 1 << tw_log2 (3 or 4), TH = 64 >> tw_log2
     int tiles_x, tiles_y;        // pixel tiles per image
     int tiles_total;             // B * tiles_y * tiles_x
     int tiles_per_split;
     int groups, G;               // channel-chunk groups of G chunks (the last group may hold fewer real chunks)
-    int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4)
-    int stages, patch_bytes, stage_bytes;
-    int npass, x_lo, d_lo;       // split-accumulate passes per tile: pass i uses lo(input) if x_lo bit i, lo(dout) if d_lo bit i
-    int stack;                   // split mode, Cout <= 64: dout in atoms 0-1 and lo(dout) in atoms 2-3 of the M-side tile, so the passes
-                                 // lo(x) and x give all four products (lanes o and 64 + o both red.add into dw): 2 MMAs instead of 3
-    int tpc;                     // pixel tiles per accumulation chain: the tensor core adds into TMEM with truncation (bias ~3e-8 per
-                                 // MMA of a chain), so the epilogue warps drain the accumulator into registers (round-to-nearest adds)
-                                 // every tpc tiles while the MMAs continue in the second TMEM buffer
+    int atoms_m;                 // 32-channel atoms of the Cout tile that are loaded (1..4; stacked: 1..2 for each of dout / lo(dout))
+    int stages, stage_bytes;
+    int split;                   // 1: split-accumulate (two stages per tile, see above); 0: plain TF32 (one stage, one pass)
+    int stack;                   // split mode with Cout <= 64: dout / lo(dout) stacked in the M part
 };
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
@@ -56,7 +63,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     uint8_t* ring = smem + 1024;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
+    const int TW = 1 << g.tw_log2, TH = WT_PIX >> g.tw_log2;
     const int cg = blockIdx.x / p.kw, dx = blockIdx.x - cg * p.kw;        // channel-chunk group, horizontal tap
     const int n0 = blockIdx.y * TBM;                                     // first output channel of this CTA
     const int t_begin = blockIdx.z * g.tiles_per_split, t_end = min(g.tiles_total, t_begin + g.tiles_per_split);
@@ -65,6 +72,9 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     const int chunk0 = cg * g.G;                                         // first 32-channel chunk of the group
     const int natoms = p.kh * g.G;                                       // N atoms of the accumulator
     const int NCOLS = natoms * 32;
+    const int spt = g.split ? 2 : 1;                                     // stages per tile
+    const int tpc = g.split ? 1 : ntiles;                                // tiles per accumulation chain
+    const int nchains = (ntiles + tpc - 1) / tpc;
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -89,37 +99,44 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
         if (lane == 0) {
             tc::tma_prefetch_desc(&xmap);
             tc::tma_prefetch_desc(&dmap);
+            if (g.split) {
+                tc::tma_prefetch_desc(&xmap_lo);
+                tc::tma_prefetch_desc(&dmap_lo);
+            }
             const int prows = TH + p.kh - 1;
             const uint32_t row_bytes = (uint32_t)(TW * 128);
-            const uint32_t tx_bytes = (uint32_t)((g.stack ? 2 : 1) * g.atoms_m * TBM * 128) + (uint32_t)(prows * g.G) * row_bytes;
+            const uint32_t n_bytes = (uint32_t)(prows * g.G) * row_bytes;
+            const uint32_t m_bytes = (uint32_t)(g.atoms_m * WT_ATOM_BYTES);
             int s = 0;
             uint32_t ph = 0;
-            // one accumulation chain = tpc tiles; inside a chain the low-part passes run first, the raw x raw pass last
-            for (int tc0 = t_begin; tc0 < t_end; tc0 += g.tpc)
-            for (int qp = 0; qp < g.npass; ++qp) {
-                const int ps = (qp + 1) % g.npass;
-                const CUtensorMap* xm = ((g.x_lo >> ps) & 1) ? &xmap_lo : &xmap;
-                const CUtensorMap* dm = ((g.d_lo >> ps) & 1) ? &dmap_lo : &dmap;
-                for (int t = tc0; t < min(t_end, tc0 + g.tpc); ++t) {
-                    int q = t;
-                    const int tx = q % g.tiles_x; q /= g.tiles_x;
-                    const int ty = q % g.tiles_y;
-                    const int b = q / g.tiles_y;
-                    const int y0 = ty * TH, x0 = tx * TW;
+            for (int t = t_begin; t < t_end; ++t) {
+                int q = t;
+                const int tx = q % g.tiles_x; q /= g.tiles_x;
+                const int ty = q % g.tiles_y;
+                const int b = q / g.tiles_y;
+                const int y0 = ty * TH, x0 = tx * TW;
+                for (int j = 0; j < spt; ++j) {
+                    // stage j of the tile: which tensors feed its M part (dout side) and its N part (input side)
+                    const CUtensorMap* xm = (g.split && j == 0) ? &xmap_lo : &xmap;       // A: lo(x);  B (or plain): x
+                    const bool load_m = !(g.stack && j == 1);                             // stacked: stage B has no M part
+                    const uint32_t m_total = load_m ? (g.stack ? 2 * m_bytes : m_bytes) : 0u;
                     tc::mbar_wait(bar_empty + s, ph ^ 1);
                     const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
-                    tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
-                    // M side: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
-                    for (int a = 0; a < g.atoms_m; ++a) {
-                        if (g.stack) {
-                            tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
-                            tc::tma_load_4d(st + (uint32_t)((2 + a) * TBM * 128), &dmap_lo, n0 + 32 * a, x0, y0, b, bar_full + s);
-                        } else {
-                            tc::tma_load_4d(st + (uint32_t)(a * TBM * 128), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                    tc::mbar_arrive_expect_tx(bar_full + s, m_total + n_bytes);
+                    if (load_m) {
+                        // M part: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
+                        for (int a = 0; a < g.atoms_m; ++a) {
+                            if (g.stack) {
+                                tc::tma_load_4d(st + (uint32_t)(a * WT_ATOM_BYTES), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
+                                tc::tma_load_4d(st + (uint32_t)((2 + a) * WT_ATOM_BYTES), &dmap_lo, n0 + 32 * a, x0, y0, b, bar_full + s);
+                            } else {
+                                const CUtensorMap* dm = (g.split && j == 1) ? &dmap_lo : &dmap;   // A (or plain): dout;  B: lo(dout)
+                                tc::tma_load_4d(st + (uint32_t)(a * WT_ATOM_BYTES), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                            }
                         }
                     }
-                    // N side: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
-                    const uint32_t pst = st + WT_DOUT_BYTES;
+                    // N part: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
+                    const uint32_t pst = st + WT_M_BYTES;
                     for (int r = 0; r < prows; ++r)
                         for (int c = 0; c < g.G; ++c)
                             tc::tma_load_4d(pst + (uint32_t)(r * g.G + c) * row_bytes, xm, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
@@ -134,34 +151,53 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(TBM, NCOLS, 1, 1);               // both operands MN-major
             // constant descriptor fields; the start address (>> 4) is added per MMA
-            const uint64_t dm0 = tc::make_smem_desc(0, TBM * 128, 512, tc::LAYOUT_SW128_BASE32B);            // atoms 16 KB apart
-            const uint64_t dn0 = tc::make_smem_desc(0, (uint32_t)(TW * 128), 512, tc::LAYOUT_SW128_BASE32B);   // atoms one (row, chunk) block apart
+            const uint64_t dm0 = tc::make_smem_desc(0, WT_ATOM_BYTES, 512, tc::LAYOUT_SW128_BASE32B);         // M atoms one dout atom apart
+            const uint64_t dn0 = tc::make_smem_desc(0, (uint32_t)(TW * 128), 512, tc::LAYOUT_SW128_BASE32B);   // N atoms one (row, chunk) block apart
             const int slices = TW >> 3;                       // 8-pixel slices per tile row
             int s = 0;
             uint32_t ph = 0;
-            int jc = 0;                                      // chains issued: TMEM buffer jc & 1
-            for (int tc0 = 0; tc0 < ntiles; tc0 += g.tpc, ++jc) {
+            int jc = 0;                                       // chains issued: TMEM buffer jc & 1
+            for (int t = 0; t < ntiles; ++t) {
+                const bool first_of_chain = t % tpc == 0;
                 const uint32_t acc = tmem_base + (uint32_t)((jc & 1) * 256);
-                tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
-                tc::fence_after_thread_sync();
-                for (int qp = 0; qp < g.npass; ++qp) {
-                    for (int t = tc0; t < min(ntiles, tc0 + g.tpc); ++t) {
-                        tc::mbar_wait(bar_full + s, ph);
+                if (first_of_chain) {
+                    tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
+                    tc::fence_after_thread_sync();
+                }
+                const int sA = s, sB = s + 1;                 // (sB only in split mode: stages is even, so it never wraps)
+                const uint32_t aM = ring_base + (uint32_t)(sA * g.stage_bytes), aN = aM + WT_M_BYTES;
+                const uint32_t bM = ring_base + (uint32_t)(sB * g.stage_bytes), bN = bM + WT_M_BYTES;
+                // passes of the tile as (M part address, N part address); the big x . dout term comes last
+                const int npass = g.split ? (g.stack ? 2 : 3) : 1;
+                for (int ps = 0; ps < npass; ++ps) {
+                    uint32_t m_addr, n_addr;
+                    if (ps == 0) {                            // A x A
+                        tc::mbar_wait(bar_full + sA, ph);
                         tc::fence_after_thread_sync();
-                        const uint32_t m_addr = ring_base + (uint32_t)(s * g.stage_bytes);
-                        const uint32_t n_addr = m_addr + WT_DOUT_BYTES;
-                        for (int r = 0; r < TH; ++r) {
-                            for (int kq = 0; kq < slices; ++kq) {
-                                const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
-                                const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
-                                tc::mma_tf32(acc, dm, dn, idesc, (qp != 0 || t != tc0 || r != 0 || kq != 0) ? 1u : 0u);
-                            }
+                        m_addr = aM; n_addr = aN;
+                    } else if (ps == 1) {
+                        tc::mbar_wait(bar_full + sB, ph);
+                        tc::fence_after_thread_sync();
+                        m_addr = g.stack ? aM : bM; n_addr = bN;      // stacked: [dout; lo(dout)] . x   |   lo(dout) . x
+                    } else {                                  // A's dout . B's x
+                        m_addr = aM; n_addr = bN;
+                    }
+                    for (int r = 0; r < TH; ++r) {
+                        for (int kq = 0; kq < slices; ++kq) {
+                            const uint64_t dm = dm0 + (uint64_t)((m_addr + (uint32_t)((r * TW + kq * 8) * 128)) >> 4);
+                            const uint64_t dn = dn0 + (uint64_t)((n_addr + (uint32_t)((r * g.G * TW + kq * 8) * 128)) >> 4);
+                            tc::mma_tf32(acc, dm, dn, idesc, (!first_of_chain || ps != 0 || r != 0 || kq != 0) ? 1u : 0u);
                         }
-                        tc::mma_commit(bar_empty + s);
-                        if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
                 }
-                tc::mma_commit(acc_full + (jc & 1));
+                tc::mma_commit(bar_empty + sA);               // both stages are free once every MMA of the tile has read them
+                if (g.split) tc::mma_commit(bar_empty + sB);
+                s += spt;
+                if (s >= g.stages) { s = 0; ph ^= 1; }
+                if ((t + 1) % tpc == 0 || t == ntiles - 1) {
+                    tc::mma_commit(acc_full + (jc & 1));
+                    ++jc;
+                }
             }
         }
         __syncwarp();
@@ -174,7 +210,6 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
         const bool real = n0 + oq * 32 < p.Cout;          // warp-uniform: this lane quarter holds real output channels
         constexpr int APW = 3;                            // accumulator atoms (32 columns) per warp: a = half + 2 * ai < kh * G <= 6
         float accr[APW][32];
-        const int nchains = (ntiles + g.tpc - 1) / g.tpc;
         for (int c = 0; c < nchains; ++c) {
             const int buf = c & 1;
             tc::mbar_wait(acc_full + buf, (c >> 1) & 1);
@@ -229,17 +264,18 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
 
 bool conv_wgrad_tma_eligible(const ScsfmConv& p) {
     return p.stride == 1 && p.pad_mode == PADMODE_ZERO && p.kh >= 1 && p.kh <= 3 && p.kw >= 1 && p.kw <= 3 && (p.Cin & 3) == 0 &&
-           (p.Cout & 3) == 0 && p.Ho == p.Hi + 2 * p.pad - p.kh + 1 && p.Wo == p.Wi + 2 * p.pad - p.kw + 1;
+           (p.Cout & 3) == 0 && p.Ho == p.Hi + 2 * p.pad - p.kh + 1 && p.Wo == p.Wi + 2 * p.pad - p.kw + 1 &&
+           ((p.in_lo != nullptr) == (p.dout_lo != nullptr));      // split mode needs both low parts
 }
 
 int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX);
     SCSFM_CHECK_CUDA(attr_rc);
     WtGeom g;
-    // tile shape: least padded area
-    const long a16 = (long)((p.Ho + 7) / 8 * 8) * ((p.Wo + 15) / 16 * 16), a8 = (long)((p.Ho + 15) / 16 * 16) * ((p.Wo + 7) / 8 * 8);
+    // tile shape (64 pixels): least padded area
+    const long a16 = (long)((p.Ho + 3) / 4 * 4) * ((p.Wo + 15) / 16 * 16), a8 = (long)((p.Ho + 7) / 8 * 8) * ((p.Wo + 7) / 8 * 8);
     g.tw_log2 = a8 < a16 ? 3 : 4;
-    const int TW = 1 << g.tw_log2, TH = TBM >> g.tw_log2;
+    const int TW = 1 << g.tw_log2, TH = WT_PIX >> g.tw_log2;
     g.tiles_x = (p.Wo + TW - 1) / TW;
     g.tiles_y = (p.Ho + TH - 1) / TH;
     g.tiles_total = g.tiles_x * g.tiles_y * p.B;
@@ -248,20 +284,23 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     g.groups = (chunks + g.G - 1) / g.G;
     const int nt = (p.Cout + TBM - 1) / TBM;
     const int cout_tile = p.Cout < TBM ? p.Cout : TBM;             // (the last Cout tile may need fewer atoms; extra rows are zero-filled)
+    g.split = (p.in_lo != nullptr && p.dout_lo != nullptr) ? 1 : 0;
+    g.stack = (g.split && p.Cout <= 64) ? 1 : 0;
     g.atoms_m = (cout_tile + 31) / 32;
-    g.patch_bytes = (TH + p.kh - 1) * g.G * TW * 128;
-    g.stage_bytes = WT_DOUT_BYTES + (g.patch_bytes + 1023) / 1024 * 1024;
+    const int patch_bytes = (TH + p.kh - 1) * g.G * TW * 128;
+    g.stage_bytes = WT_M_BYTES + (patch_bytes + 1023) / 1024 * 1024;
     g.stages = (WT_SMEM_MAX - 2048) / g.stage_bytes;
     if (g.stages > WT_MAX_STAGES) g.stages = WT_MAX_STAGES;
+    g.stages &= ~1;                                                // even: a split-mode tile takes two consecutive stages
     if (g.stages < 2) {
         set_error("conv_wgrad_tma: stage of %d bytes does not fit twice in shared memory", g.stage_bytes);
         return SCSFM_ERR_ARG;
     }
     // Split the pixel tiles over gridDim.z.  One CTA per SM is resident (shared memory), so the kernel takes
     //   waves * (tiles per CTA + fixed cost per CTA)   with waves = ceil(slices * splits / SMs):
-    // pick the split count that minimises it (the former "about two waves" rule gave e.g. 297 CTAs = 2.007 waves on 148 SMs,
+    // pick the split count that minimises it (an "about two waves" rule gave e.g. 297 CTAs = 2.007 waves on 148 SMs,
     // i.e. three waves of 13 tiles where one wave of 26 would do).  The fixed cost (prologue + red.add epilogue of a
-    // 128 x 192 partial tile) is worth about 3 tiles; at least 2 tiles per CTA.
+    // 128 x 192 partial tile) is worth about 6 of the 64-pixel tiles; at least 4 tiles per CTA.
     const int slices = g.groups * p.kw * nt;
     int nsm = 148;
     {
@@ -270,24 +309,18 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     }
     int splits = 1;
     {
-        const int max_splits = g.tiles_total >= 2 ? g.tiles_total / 2 : 1;
+        const int max_splits = g.tiles_total >= 4 ? g.tiles_total / 4 : 1;
         long best = -1;
         for (int sp = 1; sp <= max_splits && sp <= 4096; ++sp) {
             const int tps = (g.tiles_total + sp - 1) / sp;
             const int real = (g.tiles_total + tps - 1) / tps;
             const long waves = ((long)slices * real + nsm - 1) / nsm;
-            const long cost = waves * (tps + 3);
+            const long cost = waves * (tps + 6);
             if (best < 0 || cost < best) { best = cost; splits = real; }
         }
     }
     g.tiles_per_split = (g.tiles_total + splits - 1) / splits;
     splits = (g.tiles_total + g.tiles_per_split - 1) / g.tiles_per_split;
-    g.npass = 1; g.x_lo = 0; g.d_lo = 0;
-    g.stack = (p.Cout <= 64 && p.in_lo != nullptr && p.dout_lo != nullptr) ? 1 : 0;
-    if (p.in_lo != nullptr) { g.x_lo |= 1 << g.npass; ++g.npass; }
-    if (p.dout_lo != nullptr && !g.stack) { g.d_lo |= 1 << g.npass; ++g.npass; }
-    // split mode: chains of <= 96 MMAs (16 per tile and pass); plain TF32: one chain per CTA
-    g.tpc = g.npass > 1 ? (96 / (16 * g.npass) > 0 ? 96 / (16 * g.npass) : 1) : g.tiles_per_split;
     CUtensorMap xmap, dmap, xmap_lo, dmap_lo;
     for (int lo = 0; lo < 2; ++lo) {
         const float* base = lo ? p.in_lo : p.in;
