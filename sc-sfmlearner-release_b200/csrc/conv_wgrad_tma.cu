@@ -21,9 +21,10 @@
 //                                          pass 3: M = A, N = B      x . dout         (the big term last)
 //    With Cout <= 64 dout sits in atoms 0-1 and lo(dout) in atoms 2-3 of stage A's M part (both red.add into dw), stage B
 //    carries only x:  pass 1: M = A, N = A;  pass 2: M = A, N = B  -- two MMAs per K8 slice instead of three;
-//  * the tensor core adds into TMEM with truncation (bias ~3e-8 per MMA of a chain): in split mode every tile is its own
-//    accumulation chain, drained by the epilogue warps into registers (round-to-nearest adds) while the MMAs of the next
-//    tile run in the second TMEM buffer; plain TF32: one chain per CTA;
+//  * the tensor core adds into TMEM with truncation (bias ~3e-8 per MMA of a chain): in split mode an accumulation chain is
+//    2-3 tiles (48 MMAs), drained by the epilogue warps into registers (round-to-nearest adds) while the MMAs of the next
+//    chain run in the second TMEM buffer (one tile per chain starves the MMAs: a drain takes about as long as 16 MMAs);
+//    plain TF32: one chain per CTA;
 //  * split-K over pixel-tile ranges (gridDim.z, wave-aware count), fp32 vector red.add of the partial dW tiles.
 // Reflection-padded layers (beyond the zero-padded pass), stride 2 and kernels larger than 3x3 stay on the cp.async kernel.
 #include "conv_tc.cuh"
@@ -48,6 +49,7 @@ struct WtGeom {
     int stages, stage_bytes;
     int split;                   // 1: split-accumulate (two stages per tile, see above); 0: plain TF32 (one stage, one pass)
     int stack;                   // split mode with Cout <= 64: dout / lo(dout) stacked in the M part
+    int tpc;                     // tiles per accumulation chain (split mode: 2-3 tiles = 48 MMAs; plain TF32: the whole CTA)
 };
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
@@ -73,7 +75,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     const int natoms = p.kh * g.G;                                       // N atoms of the accumulator
     const int NCOLS = natoms * 32;
     const int spt = g.split ? 2 : 1;                                     // stages per tile
-    const int tpc = g.split ? 1 : ntiles;                                // tiles per accumulation chain
+    const int tpc = g.split ? g.tpc : ntiles;                            // tiles per accumulation chain
     const int nchains = (ntiles + tpc - 1) / tpc;
 
     if (tid == 0) {
@@ -286,6 +288,7 @@ int launch_conv_wgrad_tma(const ScsfmConv& p, cudaStream_t st) {
     const int cout_tile = p.Cout < TBM ? p.Cout : TBM;             // (the last Cout tile may need fewer atoms; extra rows are zero-filled)
     g.split = (p.in_lo != nullptr && p.dout_lo != nullptr) ? 1 : 0;
     g.stack = (g.split && p.Cout <= 64) ? 1 : 0;
+    g.tpc = g.stack ? 3 : 2;
     g.atoms_m = (cout_tile + 31) / 32;
     const int patch_bytes = (TH + p.kh - 1) * g.G * TW * 128;
     g.stage_bytes = WT_M_BYTES + (patch_bytes + 1023) / 1024 * 1024;
