@@ -22,7 +22,9 @@
 
 namespace scsfm {
 
-template <int BN>
+// STACK = true (split mode, Cout <= BN / 2): the weight tile holds W in rows [0, BN/2) and lo(W) in rows [BN/2, BN), so the two
+// passes lo(in) and in give all four products (accumulator columns n and BN/2 + n are added in the epilogue): 2 passes, not 3.
+template <int BN, bool STACK = false>
 __global__ void __launch_bounds__(FW_THREADS)
 conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap wmap_lo) {
     using Cfg = TcCfg<BN>;
@@ -42,7 +44,7 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
     const int KB = (K + TBK - 1) / TBK;
     // split-accumulate passes over the whole K range (ScsfmConv.in_lo / w_lo): raw x raw, lo(in) x raw(w), raw(in) x lo(w)
-    const int npass = 1 + (p.in_lo != nullptr ? 1 : 0) + (p.w_lo != nullptr ? 1 : 0);
+    const int npass = STACK ? 2 : 1 + (p.in_lo != nullptr ? 1 : 0) + (p.w_lo != nullptr ? 1 : 0);
     // round-robin accumulators only in split mode (plain TF32 is bounded by its operand rounding: one accumulator, fewer TMEM
     // columns, more resident CTAs)
     const int nacc_rt = npass > 1 ? Cfg::NACC : 1;
@@ -125,7 +127,12 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
                 // weights: TMA box (32 K-columns x BN rows) straight into the 128B-swizzled stage; rows / columns beyond
                 // Cout / K are zero-filled by the hardware and still count towards the expected bytes
                 tc::mbar_arrive_expect_tx(bar_full + s, (uint32_t)Cfg::B_STAGE_BYTES);
-                tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), wm, kb * TBK, n0, bar_full + s);
+                if (STACK) {
+                    tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), &wmap, kb * TBK, 0, bar_full + s);
+                    tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES + (BN / 2) * 128), &wmap_lo, kb * TBK, 0, bar_full + s);
+                } else {
+                    tc::tma_load_2d(b_smem + (uint32_t)(s * Cfg::B_STAGE_BYTES), wm, kb * TBK, n0, bar_full + s);
+                }
             }
             if (dy != cur_dy || dx != cur_dx) {
                 cur_dy = dy; cur_dx = dx;
@@ -177,22 +184,29 @@ conv_fwd_tc_kernel(ScsfmConv p, TcView v, const __grid_constant__ CUtensorMap wm
             out_row = ((size_t)b * v.out_H + (ho * v.out_sy + v.out_oy)) * v.out_W + (wo * v.out_sx + v.out_ox);
         }
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // all MMAs retired: operand smem is free
-        constexpr int CW = BN < 32 ? BN : 32;
+        constexpr int CREAL = STACK ? BN / 2 : BN;                // accumulator columns holding output channels
+        constexpr int CW = CREAL < 32 ? CREAL : 32;
         const int nacc = min(nacc_rt, KB * npass);              // accumulators that received at least one k-block
+        constexpr int NCH = CREAL / CW;                           // column chunks of real output channels
 #pragma unroll 1
-        for (int cc = half; cc < BN / CW; cc += FW_PWARPS / 4) {
+        for (int cc = half; cc < NCH; cc += FW_PWARPS / 4) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * CW);
             if (CW == 32) tc::tmem_ld32(taddr, r);
             else tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
-            for (int a = 1; a < nacc; ++a) {                   // the round-robin partial accumulators, added in fp32 (RN)
-                uint32_t q[32];
-                if (CW == 32) tc::tmem_ld32(taddr + (uint32_t)(a * Cfg::ACC_COLS), q);
-                else tc::tmem_ld16(taddr + (uint32_t)(a * Cfg::ACC_COLS), q);
-                tc::tmem_ld_wait();
+            // the round-robin partial accumulators (and, stacked, the lo(W) columns BN/2 further on), added in fp32 (RN)
+            for (int a = 0; a < nacc; ++a) {
+                for (int h = 0; h < (STACK ? 2 : 1); ++h) {
+                    if (a == 0 && h == 0) continue;
+                    uint32_t q[32];
+                    const uint32_t src = taddr + (uint32_t)(a * Cfg::ACC_COLS + h * (BN / 2));
+                    if (CW == 32) tc::tmem_ld32(src, q);
+                    else tc::tmem_ld16(src, q);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+                    for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+                }
             }
             float v[32];
 #pragma unroll
@@ -575,10 +589,10 @@ static TcView plain_view(const ScsfmConv& p) {
     return TcView{p.kh, p.kw, -p.pad, -p.pad, p.stride, 1, 0, 1, 0, p.Ho, p.Wo};
 }
 
-template <int BN>
+template <int BN, bool STACK = false>
 static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
-    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_fwd_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_fwd_tc_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     SCSFM_CHECK_CUDA(attr_rc);
     const int M = p.B * (v.border ? border_count(p.Ho, p.Wo) : p.Ho * p.Wo);
     // TMA descriptor of the weight matrix [Cout rows][K columns] (K contiguous), box = 32 columns x BN rows, 128B swizzle
@@ -590,7 +604,7 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
         if (base == nullptr) { wmap_lo = wmap; continue; }
         const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)p.Cout};
         const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
-        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BN};
+        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)(STACK ? BN / 2 : BN)};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode_tiled(&wmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -600,8 +614,8 @@ static int launch_fwd_tc(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
             return SCSFM_ERR_CUDA;
         }
     }
-    dim3 grid((M + TBM - 1) / TBM, (p.Cout + BN - 1) / BN);
-    conv_fwd_tc_kernel<BN><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, v, wmap, wmap_lo);
+    dim3 grid((M + TBM - 1) / TBM, STACK ? 1 : (p.Cout + BN - 1) / BN);
+    conv_fwd_tc_kernel<BN, STACK><<<grid, FW_THREADS, Cfg::SMEM, st>>>(p, v, wmap, wmap_lo);
     SCSFM_CHECK_LAUNCH();
     return SCSFM_OK;
 }
@@ -613,6 +627,11 @@ using namespace scsfm;
 // cp.async gather kernel: any stride / padding mode / border-only rows
 static int tc_dispatch_gather(const ScsfmConv& p, const TcView& v, cudaStream_t st) {
     const int N = p.Cout;
+    if (p.in_lo != nullptr && p.w_lo != nullptr && N <= 64) {       // split mode, thin: W / lo(W) stacked on the N side
+        if (N <= 16) return launch_fwd_tc<32, true>(p, v, st);
+        if (N <= 32) return launch_fwd_tc<64, true>(p, v, st);
+        return launch_fwd_tc<128, true>(p, v, st);
+    }
     if (N <= 16) return launch_fwd_tc<16>(p, v, st);
     if (N <= 32 || N % 64 != 0) return launch_fwd_tc<32>(p, v, st);
     if (N <= 64 || N % 128 != 0) return launch_fwd_tc<64>(p, v, st);
@@ -825,7 +844,7 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
         const bool split = p->in_lo != nullptr || p->dout_lo != nullptr;
         // (measured per layer, profiles/r02_layers_tf32x3.txt: from 128 output channels up the TMA kernel wins; at 64 the
         // cp.async kernel with dout / lo(dout) stacked on its N side does)
-        kernel = (split && p->Cout > 64) ? 2 : 1;
+        kernel = (split && (p->Cout > 64 || (p->Cout == 64 && p->pad_mode == PADMODE_ZERO))) ? 2 : 1;
     }
     if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
