@@ -219,11 +219,12 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     B = cfg["batch"]
 
-    def make_trainer(mode):
+    def make_trainer(mode, overlap=True):
         torch.manual_seed(0)
         disp, pose = models.DispResNet(cfg["dl"], False).to(dev).train(), models.PoseResNet(cfg["pl"], False).to(dev).train()
         return Trainer(disp, pose, lr=1e-4, num_scales=1, with_ssim=1, with_mask=1, with_auto_mask=1, padding_mode="zeros",
-                       w1=1.0, w2=0.1, w3=0.5, distributed=world > 1, conv_mode=mode, overlap_nets=bool(args.overlap_nets), overlap_wgrad=bool(args.overlap_wgrad))
+                       w1=1.0, w2=0.1, w3=0.5, distributed=world > 1, conv_mode=mode, overlap_nets=overlap and bool(args.overlap_nets),
+                       overlap_wgrad=overlap and bool(args.overlap_wgrad))
 
     def barrier():
         if world > 1:
@@ -247,7 +248,10 @@ def run_ours(args):
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
         return float(total)
 
-    trainer = make_trainer(args.conv_mode)
+    # The per-family / per-kernel passes run the step SERIALLY (one stream): CUDA events around a launch only measure that
+    # kernel when nothing else runs beside it.  The timed region below uses the overlapped step (two networks and the weight
+    # gradients on side streams).
+    trainer = make_trainer(args.conv_mode, overlap=False)
     # ---- warm-up with full per-family profiling: finds the dominant kernel family and times the loss kernels ------
     trainer.step(d_tgt, d_refs, d_K)          # first step unprofiled: lazy kernel loading, allocations, Adam state
     torch.cuda.synchronize()
@@ -287,6 +291,10 @@ def run_ours(args):
     dom_work = sum(e[1] for e in L.PROF["events"])
     dom_n = len(L.PROF["events"])
     L.PROF.update(enabled=False, only=None, events=[])
+    del trainer
+    trainer = make_trainer(args.conv_mode)
+    for _ in range(2):
+        trainer.step(d_tgt, d_refs, d_K)
 
     # ---- timed region: device-resident inputs; the whole step is one CUDA-graph replay ---------
     def capture(tr):
@@ -375,6 +383,7 @@ def run_ours(args):
     roof.update(kernel=dominant, launches_timed=dom_n, avg_launch_us=round(1e3 * dom_ms / max(dom_n, 1), 2),
                 algorithmic_flops_or_bytes_per_launch=round(dom_work / max(dom_n, 1)),
                 share_of_step=round(dom_ms / ms_eager, 4), peak_source=peaks["source"],
+                share_note="share of the SERIAL eager step (one stream); the timed step overlaps the two networks and the weight gradients",
                 note="achieved = ALGORITHMIC FLOPs (2*M*N*K per conv pass, the same count in every conv mode: the 3 split-accumulate "
                      "products of tf32x3 are not counted as extra work) or bytes of the family / its CUDA-event time over the same K "
                      "steps run eagerly (events cannot be recorded inside the replayed CUDA graph); sustained bf16 peak is the "
@@ -388,7 +397,7 @@ def run_ours(args):
         "config": {"workload": cfg["label"], "name": args.config, "global_batch": B * world, "height": cfg["H"], "width": cfg["W"],
                    "n_ref": cfg["n_ref"], "parallelism": "dp%d" % world, "conv_mode": args.conv_mode,
                    "l2": "flushed (256 MiB write) before every step", "cuda_graph": graphed, "overlap_nets": bool(args.overlap_nets), "overlap_wgrad": bool(args.overlap_wgrad),
-                   "eager_ms_per_step": round(ms_eager / args.steps, 3), "loss_flags": "num_scales=1 ssim=1 mask=1 auto_mask=1 zeros"},
+                   "serial_eager_ms_per_step": round(ms_eager / args.steps, 3), "loss_flags": "num_scales=1 ssim=1 mask=1 auto_mask=1 zeros"},
         "e2e": {"value": round(frames / (ms_e2e * 1e-3), 3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
