@@ -118,3 +118,33 @@ def test_validate_with_gt_matches_the_oracle():
             out = torch.nn.functional.interpolate(out.unsqueeze(1), [100, 140]).squeeze(1)
             want += np.array(OL.compute_errors(depth, out, "kitti"))
     np.testing.assert_allclose(got, want / 2, rtol=2e-3, atol=1e-6)
+
+
+def test_train_entry_end_to_end_on_synthetic_data(tmp_path):
+    """`python train.py synthetic ...` with the reference's flags: two epochs of three iterations (CUDA-graph step, async logging:
+    one read-back per print interval), validation after every epoch, checkpoints and the reference's log files
+    (train.py:219-232,270-290; utils.py:57-66)."""
+    import csv
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "sc-sfmlearner-release_b200", "train.py"), "synthetic", "--name", "e2e", "--epochs", "2",
+           "--epoch-size", "3", "-b", "2", "--synthetic-size", "128", "160", "--resnet-layers", "18", "--num-scales", "1", "-s", "0.1", "-c", "0.5",
+           "--sequence-length", "3", "--with-ssim", "1", "--with-mask", "1", "--with-auto-mask", "1", "--with-pretrain", "0", "--print-freq", "2"]
+    out = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert " * epoch 1 train loss" in out.stdout
+    runs = os.listdir(tmp_path / "checkpoints" / "e2e")
+    assert len(runs) == 1
+    d = tmp_path / "checkpoints" / "e2e" / runs[0]
+    files = set(os.listdir(d))
+    assert {"dispnet_checkpoint.pth.tar", "exp_pose_checkpoint.pth.tar", "dispnet_model_best.pth.tar", "exp_pose_model_best.pth.tar",
+            "progress_log_summary.csv", "progress_log_full.csv"} <= files
+    full = list(csv.reader(open(d / "progress_log_full.csv"), delimiter="\t"))
+    assert full[0] == ["train_loss", "photo_loss", "smooth_loss", "geometry_consistency_loss"] and len(full) == 1 + 2 * 3
+    assert all(np.isfinite(float(v)) for row in full[1:] for v in row)
+    summary = list(csv.reader(open(d / "progress_log_summary.csv"), delimiter="\t"))
+    assert summary[0] == ["train_loss", "validation_loss"] and len(summary) == 3
+    ck = torch.load(d / "dispnet_checkpoint.pth.tar")
+    assert ck["epoch"] == 2 and "encoder.encoder.conv1.weight" in ck["state_dict"]
