@@ -77,6 +77,10 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     const int spt = g.split ? 2 : 1;                                     // stages per tile
     const int tpc = g.split ? g.tpc : ntiles;                            // tiles per accumulation chain
     const int nchains = (ntiles + tpc - 1) / tpc;
+    // optional per-CTA cycle counters (ScsfmConv.debug, 8 per CTA): [0] producer waiting for a free stage, [1] producer total,
+    // [2] MMA thread waiting for operands, [3] MMA thread waiting for a drained accumulator, [4] MMA thread total,
+    // [5] epilogue warp 0 waiting for a chain, [6] epilogue total, [7] tiles
+    unsigned long long* dbg = p.debug ? p.debug + 8 * (size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -111,6 +115,8 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             const uint32_t m_bytes = (uint32_t)(g.atoms_m * WT_ATOM_BYTES);
             int s = 0;
             uint32_t ph = 0;
+            long long tw = 0;
+            const long long tb = clock64();
             for (int t = t_begin; t < t_end; ++t) {
                 int q = t;
                 const int tx = q % g.tiles_x; q /= g.tiles_x;
@@ -122,7 +128,9 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                     const CUtensorMap* xm = (g.split && j == 0) ? &xmap_lo : &xmap;       // A: lo(x);  B (or plain): x
                     const bool load_m = !(g.stack && j == 1);                             // stacked: stage B has no M part
                     const uint32_t m_total = load_m ? (g.stack ? 2 * m_bytes : m_bytes) : 0u;
+                    const long long t0 = dbg ? clock64() : 0;
                     tc::mbar_wait(bar_empty + s, ph ^ 1);
+                    if (dbg) tw += clock64() - t0;
                     const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
                     tc::mbar_arrive_expect_tx(bar_full + s, m_total + n_bytes);
                     if (load_m) {
@@ -146,6 +154,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                     if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
             }
+            if (dbg) { dbg[0] = (unsigned long long)tw; dbg[1] = (unsigned long long)(clock64() - tb); }
         }
         __syncwarp();
     } else if (warp == WT_EWARPS + 1) {
@@ -159,11 +168,15 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             int s = 0;
             uint32_t ph = 0;
             int jc = 0;                                       // chains issued: TMEM buffer jc & 1
+            long long tfull = 0, tacc = 0;
+            const long long tb = clock64();
             for (int t = 0; t < ntiles; ++t) {
                 const bool first_of_chain = t % tpc == 0;
                 const uint32_t acc = tmem_base + (uint32_t)((jc & 1) * 256);
                 if (first_of_chain) {
+                    const long long t0 = dbg ? clock64() : 0;
                     tc::mbar_wait(acc_empty + (jc & 1), ((jc >> 1) & 1) ^ 1);      // drained by the epilogue warps
+                    if (dbg) tacc += clock64() - t0;
                     tc::fence_after_thread_sync();
                 }
                 const int sA = s, sB = s + 1;                 // (sB only in split mode: stages is even, so it never wraps)
@@ -173,12 +186,15 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                 const int npass = g.split ? (g.stack ? 2 : 3) : 1;
                 for (int ps = 0; ps < npass; ++ps) {
                     uint32_t m_addr, n_addr;
+                    const long long t0 = dbg ? clock64() : 0;
                     if (ps == 0) {                            // A x A
                         tc::mbar_wait(bar_full + sA, ph);
+                        if (dbg) tfull += clock64() - t0;
                         tc::fence_after_thread_sync();
                         m_addr = aM; n_addr = aN;
                     } else if (ps == 1) {
                         tc::mbar_wait(bar_full + sB, ph);
+                        if (dbg) tfull += clock64() - t0;
                         tc::fence_after_thread_sync();
                         m_addr = g.stack ? aM : bM; n_addr = bN;      // stacked: [dout; lo(dout)] . x   |   lo(dout) . x
                     } else {                                  // A's dout . B's x
@@ -201,6 +217,10 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                     ++jc;
                 }
             }
+            if (dbg) {
+                dbg[2] = (unsigned long long)tfull; dbg[3] = (unsigned long long)tacc; dbg[4] = (unsigned long long)(clock64() - tb);
+                dbg[7] = (unsigned long long)ntiles;
+            }
         }
         __syncwarp();
     } else {
@@ -212,9 +232,13 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
         const bool real = n0 + oq * 32 < p.Cout;          // warp-uniform: this lane quarter holds real output channels
         constexpr int APW = 3;                            // accumulator atoms (32 columns) per warp: a = half + 2 * ai < kh * G <= 6
         float accr[APW][32];
+        long long tw = 0;
+        const long long tb = clock64();
         for (int c = 0; c < nchains; ++c) {
             const int buf = c & 1;
+            const long long t0 = dbg ? clock64() : 0;
             tc::mbar_wait(acc_full + buf, (c >> 1) & 1);
+            if (dbg) tw += clock64() - t0;
             tc::fence_after_thread_sync();
             if (real) {
                 const uint32_t src = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
@@ -239,6 +263,7 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + buf);
         }
+        if (dbg && tid == 0) { dbg[5] = (unsigned long long)tw; dbg[6] = (unsigned long long)(clock64() - tb); }
         if (real) {
 #pragma unroll
             for (int ai = 0; ai < APW; ++ai) {

@@ -91,7 +91,7 @@ def main():
     g = torch.Generator().manual_seed(0)
     bad = 0
     totals = {(c, p): 0.0 for c, _ in cfgs for p in passes}
-    names = ["epi tmem-ld", "prod total", "mma wait-full", "mma wait-acc", "mma total", "epi wait-acc", "epi total", "tiles"]
+    names = ["epi tmem-ld | prod wait-empty (wgrad)", "prod total", "mma wait-full", "mma wait-acc", "mma total", "epi wait-acc", "epi total", "tiles"]
     for (name, B, H, W, Cin, Cout, k, s, pad, reflect) in LAYERS:
         if args.only and args.only not in name:
             continue
@@ -153,13 +153,13 @@ def main():
                     bad += 1
                 print("%-18s B%-2d %3dx%-3d C%4d->%-3d k%d s%d %-5s %-5s err %.1e  %8.3f ms %7.1f TF/s%s"
                       % (name, B, H, W, Cin, Cout, k, s, p, cname, err, t, flops / t / 1e9, msg), flush=True)
-                if args.roles and p in ("fwd", "dgrad"):
-                    dbg = torch.zeros(nsm * 8, dtype=torch.int64, device="cuda")
+                if args.roles:
+                    dbg = torch.zeros(8192 * 8, dtype=torch.int64, device="cuda")
                     cx.debug = dbg
                     run(p)
                     torch.cuda.synchronize()
                     cx.debug = None
-                    d_ = dbg.view(nsm, 8).double()
+                    d_ = dbg.view(-1, 8).double()
                     d_ = d_[d_[:, 7] > 0]
                     if d_.shape[0]:
                         m = d_.mean(0)
