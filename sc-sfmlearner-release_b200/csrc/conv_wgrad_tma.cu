@@ -101,7 +101,10 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
     const uint32_t ring_base = tc::smem_u32(ring);
 
     if (warp == WT_EWARPS) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (the whole warp)
+        // Measured with the per-role counters (profiles/r02_wgrad_roles.txt): ONE thread issuing the 14-28 TMA boxes of a stage
+        // spends ~190 cycles per cp.async.bulk.tensor and starves the MMA thread (41 % of its time waiting for operands).  So
+        // lane 0 waits for the free stage and posts the expected byte count, then the 32 lanes issue the boxes in parallel.
         if (lane == 0) {
             tc::tma_prefetch_desc(&xmap);
             tc::tma_prefetch_desc(&dmap);
@@ -109,53 +112,55 @@ conv_wgrad_tma_kernel(ScsfmConv p, WtGeom g, const __grid_constant__ CUtensorMap
                 tc::tma_prefetch_desc(&xmap_lo);
                 tc::tma_prefetch_desc(&dmap_lo);
             }
-            const int prows = TH + p.kh - 1;
-            const uint32_t row_bytes = (uint32_t)(TW * 128);
-            const uint32_t n_bytes = (uint32_t)(prows * g.G) * row_bytes;
-            const uint32_t m_bytes = (uint32_t)(g.atoms_m * WT_ATOM_BYTES);
-            int s = 0;
-            uint32_t ph = 0;
-            long long tw = 0;
-            const long long tb = clock64();
-            for (int t = t_begin; t < t_end; ++t) {
-                int q = t;
-                const int tx = q % g.tiles_x; q /= g.tiles_x;
-                const int ty = q % g.tiles_y;
-                const int b = q / g.tiles_y;
-                const int y0 = ty * TH, x0 = tx * TW;
-                for (int j = 0; j < spt; ++j) {
-                    // stage j of the tile: which tensors feed its M part (dout side) and its N part (input side)
-                    const CUtensorMap* xm = (g.split && j == 0) ? &xmap_lo : &xmap;       // A: lo(x);  B (or plain): x
-                    const bool load_m = !(g.stack && j == 1);                             // stacked: stage B has no M part
-                    const uint32_t m_total = load_m ? (g.stack ? 2 * m_bytes : m_bytes) : 0u;
+        }
+        const int prows = TH + p.kh - 1;
+        const uint32_t row_bytes = (uint32_t)(TW * 128);
+        const uint32_t n_bytes = (uint32_t)(prows * g.G) * row_bytes;
+        const uint32_t m_bytes = (uint32_t)(g.atoms_m * WT_ATOM_BYTES);
+        int s = 0;
+        uint32_t ph = 0;
+        long long tw = 0;
+        const long long tb = clock64();
+        for (int t = t_begin; t < t_end; ++t) {
+            int q = t;
+            const int tx = q % g.tiles_x; q /= g.tiles_x;
+            const int ty = q % g.tiles_y;
+            const int b = q / g.tiles_y;
+            const int y0 = ty * TH, x0 = tx * TW;
+            for (int j = 0; j < spt; ++j) {
+                // stage j of the tile: which tensors feed its M part (dout side) and its N part (input side)
+                const CUtensorMap* xm = (g.split && j == 0) ? &xmap_lo : &xmap;       // A: lo(x);  B (or plain): x
+                const bool load_m = !(g.stack && j == 1);                             // stacked: stage B has no M part
+                const int m_ops = load_m ? (g.stack ? 2 * g.atoms_m : g.atoms_m) : 0;
+                const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
+                if (lane == 0) {
                     const long long t0 = dbg ? clock64() : 0;
                     tc::mbar_wait(bar_empty + s, ph ^ 1);
                     if (dbg) tw += clock64() - t0;
-                    const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
-                    tc::mbar_arrive_expect_tx(bar_full + s, m_total + n_bytes);
-                    if (load_m) {
-                        // M part: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
-                        for (int a = 0; a < g.atoms_m; ++a) {
-                            if (g.stack) {
-                                tc::tma_load_4d(st + (uint32_t)(a * WT_ATOM_BYTES), &dmap, n0 + 32 * a, x0, y0, b, bar_full + s);
-                                tc::tma_load_4d(st + (uint32_t)((2 + a) * WT_ATOM_BYTES), &dmap_lo, n0 + 32 * a, x0, y0, b, bar_full + s);
-                            } else {
-                                const CUtensorMap* dm = (g.split && j == 1) ? &dmap_lo : &dmap;   // A (or plain): dout;  B: lo(dout)
-                                tc::tma_load_4d(st + (uint32_t)(a * WT_ATOM_BYTES), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
-                            }
-                        }
-                    }
-                    // N part: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
-                    const uint32_t pst = st + WT_M_BYTES;
-                    for (int r = 0; r < prows; ++r)
-                        for (int c = 0; c < g.G; ++c)
-                            tc::tma_load_4d(pst + (uint32_t)(r * g.G + c) * row_bytes, xm, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
-                                            bar_full + s);
-                    if (++s == g.stages) { s = 0; ph ^= 1; }
+                    tc::mbar_arrive_expect_tx(bar_full + s, (uint32_t)m_ops * WT_ATOM_BYTES + n_bytes);
                 }
+                __syncwarp();
+                const int n_ops = prows * g.G;
+                for (int k = lane; k < m_ops + n_ops; k += 32) {
+                    if (k < m_ops) {
+                        // M part: dout tile, one box (32 channels x TW x TH) per atom -> [atom][pixel][32]
+                        int a, slot;
+                        const CUtensorMap* dm;
+                        if (g.stack) { a = k >> 1; slot = (k & 1) ? 2 + a : a; dm = (k & 1) ? &dmap_lo : &dmap; }
+                        else { a = k; slot = k; dm = (g.split && j == 1) ? &dmap_lo : &dmap; }      // A (or plain): dout;  B: lo(dout)
+                        tc::tma_load_4d(st + (uint32_t)(slot * WT_ATOM_BYTES), dm, n0 + 32 * a, x0, y0, b, bar_full + s);
+                    } else {
+                        // N part: input rows shifted by dx, [row][chunk][x][32]; channels / pixels outside the tensor are zero-filled
+                        const int rc = k - m_ops, r = rc / g.G, c = rc - r * g.G;
+                        tc::tma_load_4d(st + WT_M_BYTES + (uint32_t)rc * row_bytes, xm, 32 * (chunk0 + c), x0 - p.pad + dx, y0 - p.pad + r, b,
+                                        bar_full + s);
+                    }
+                }
+                if (++s == g.stages) { s = 0; ph ^= 1; }
             }
-            if (dbg) { dbg[0] = (unsigned long long)tw; dbg[1] = (unsigned long long)(clock64() - tb); }
         }
+        (void)m_bytes;
+        if (dbg && lane == 0) { dbg[0] = (unsigned long long)tw; dbg[1] = (unsigned long long)(clock64() - tb); }
         __syncwarp();
     } else if (warp == WT_EWARPS + 1) {
         // ------------------------------------------------------------------ MMA issuer
