@@ -112,64 +112,59 @@ conv_tma_kernel(ScsfmConv p, TcView v, TmaGeom g, const __grid_constant__ CUtens
     const uint32_t ring_base = tc::smem_u32(ring);
 
     if (warp == TMA_EWARPS) {
-        // ------------------------------------------------------------------ TMA producer (the whole warp)
-        // lane 0 waits for the free stage and posts the expected byte count, then lanes 0 .. nops-1 issue one box each: a single
-        // thread spends ~190 cycles per cp.async.bulk.tensor (measured on the weight-gradient kernel, profiles/r02_wgrad_roles.txt)
+        // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             tc::tma_prefetch_desc(&amap);
             tc::tma_prefetch_desc(&wmap);
             if (g.a_lo) tc::tma_prefetch_desc(&amap_lo);
-            if (g.w_lo || g.stack) tc::tma_prefetch_desc(&wmap_lo);
-        }
-        const uint32_t tx_bytes = (uint32_t)(patch_rows * TW * 128 + v.kh * (g.stack ? 2 : 1) * BNW * 128);
-        const int wops = v.kh * (g.stack ? 2 : 1);            // weight boxes per stage
-        int s = 0;
-        uint32_t ph = 0;
-        long long t_wait = 0;
-        const long long t_begin = tma_clock();
-        for (int w = blockIdx.x; w < g.num_work; w += gridDim.x) {
-            int t = w / g.n_tiles;
-            const int n0 = (w - t * g.n_tiles) * TBM;
-            const int tx = t % g.tiles_x; t /= g.tiles_x;
-            const int ty = t % g.tiles_y;
-            const int b = t / g.tiles_y;
-            const int y0 = ty * (MT * TH) + v.oy0, x0 = tx * TW + v.ox0;
-            // one accumulation chain = cpg channel chunks; inside a chain the low-part passes run FIRST (their sums are
-            // 2^-11 of the main term: added while the accumulator is still small they lose nothing to its truncation),
-            // the raw x raw pass last
-            for (int ck0 = 0; ck0 < chunks; ck0 += g.cpg)
-            for (int q = 0; q < g.npass; ++q) {
-                const int ps = (q + 1) % g.npass;
-                const CUtensorMap* am = ((g.a_lo >> ps) & 1) ? &amap_lo : &amap;
-                const CUtensorMap* wm = ((g.w_lo >> ps) & 1) ? &wmap_lo : &wmap;
-                for (int ck = ck0; ck < min(chunks, ck0 + g.cpg); ++ck) {
-                    for (int dx = 0; dx < v.kw; ++dx) {
-                        const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
-                        if (lane == 0) {
+            if (g.w_lo) tc::tma_prefetch_desc(&wmap_lo);
+            const uint32_t tx_bytes = (uint32_t)(patch_rows * TW * 128 + v.kh * (g.stack ? 2 : 1) * BNW * 128);
+            int s = 0;
+            uint32_t ph = 0;
+            long long t_wait = 0;
+            const long long t_begin = tma_clock();
+            for (int w = blockIdx.x; w < g.num_work; w += gridDim.x) {
+                int t = w / g.n_tiles;
+                const int n0 = (w - t * g.n_tiles) * TBM;
+                const int tx = t % g.tiles_x; t /= g.tiles_x;
+                const int ty = t % g.tiles_y;
+                const int b = t / g.tiles_y;
+                const int y0 = ty * (MT * TH) + v.oy0, x0 = tx * TW + v.ox0;
+                // one accumulation chain = cpg channel chunks; inside a chain the low-part passes run FIRST (their sums are
+                // 2^-11 of the main term: added while the accumulator is still small they lose nothing to its truncation),
+                // the raw x raw pass last
+                for (int ck0 = 0; ck0 < chunks; ck0 += g.cpg)
+                for (int q = 0; q < g.npass; ++q) {
+                    const int ps = (q + 1) % g.npass;
+                    const CUtensorMap* am = ((g.a_lo >> ps) & 1) ? &amap_lo : &amap;
+                    const CUtensorMap* wm = ((g.w_lo >> ps) & 1) ? &wmap_lo : &wmap;
+                    for (int ck = ck0; ck < min(chunks, ck0 + g.cpg); ++ck) {
+                        for (int dx = 0; dx < v.kw; ++dx) {
                             const long long t0 = g.dbg ? tma_clock() : 0;
                             tc::mbar_wait(bar_empty + s, ph ^ 1);
                             if (g.dbg) t_wait += tma_clock() - t0;
+                            const uint32_t st = ring_base + (uint32_t)(s * g.stage_bytes);
                             tc::mbar_arrive_expect_tx(bar_full + s, tx_bytes);
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
                             tc::tma_load_4d(st, am, ck * TBK, x0 + dx, y0, b, bar_full + s);
-                        } else if (lane <= wops) {
-                            const int k = lane - 1;
-                            const int dy = g.stack ? (k >> 1) : k;
-                            const uint32_t wdst = st + (uint32_t)(g.a_bytes + dy * W_TILE);
-                            const int kcol = (dy * v.kw + dx) * p.Cin + ck * TBK;
-                            if (g.stack) tc::tma_load_2d(wdst + (uint32_t)((k & 1) * 64 * 128), (k & 1) ? &wmap_lo : &wmap, kcol, n0, bar_full + s);
-                            else tc::tma_load_2d(wdst, wm, kcol, n0, bar_full + s);
+                            for (int dy = 0; dy < v.kh; ++dy) {
+                                const uint32_t wdst = st + (uint32_t)(g.a_bytes + dy * W_TILE);
+                                const int kcol = (dy * v.kw + dx) * p.Cin + ck * TBK;
+                                if (g.stack) {
+                                    tc::tma_load_2d(wdst, &wmap, kcol, n0, bar_full + s);
+                                    tc::tma_load_2d(wdst + 64 * 128, &wmap_lo, kcol, n0, bar_full + s);
+                                } else {
+                                    tc::tma_load_2d(wdst, wm, kcol, n0, bar_full + s);
+                                }
+                            }
+                            if (++s == g.stages) { s = 0; ph ^= 1; }
                         }
-                        if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
                 }
             }
-        }
-        if (g.dbg && lane == 0) {
-            g.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_wait;
-            g.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(tma_clock() - t_begin);
+            if (g.dbg) {
+                g.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_wait;
+                g.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(tma_clock() - t_begin);
+            }
         }
         __syncwarp();
     } else if (warp == TMA_EWARPS + 1) {
