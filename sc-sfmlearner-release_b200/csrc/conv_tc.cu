@@ -842,9 +842,9 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
         // split-K to bound the truncation bias; the cp.async kernel does (cheap only when dW is small, i.e. thin layers).
         // Plain TF32: the cp.async kernel is as fast or faster everywhere (profiles/r02_wgrad_tma_check.txt).
         const bool split = p->in_lo != nullptr || p->dout_lo != nullptr;
-        // (measured per layer, profiles/r02_layers_tf32x3.txt: from 128 output channels up the TMA kernel wins; at 64 the
-        // cp.async kernel with dout / lo(dout) stacked on its N side does)
-        kernel = (split && (p->Cout > 64 || (p->Cout == 64 && p->pad_mode == PADMODE_ZERO))) ? 2 : 1;
+        // (measured per layer, profiles/r02_layers_tf32x3_wgrad.txt: from 64 output channels up the TMA kernel wins, below
+        // that the cp.async kernel with dout / lo(dout) stacked on its N side)
+        kernel = (split && p->Cout >= 64) ? 2 : 1;
     }
     if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
