@@ -11,6 +11,10 @@ import torch
 from . import lib as L
 
 
+_NO_IMAGE_GRAD = ("%s: gradients with respect to the IMAGES are not implemented (the training path never needs them: the reference "
+                  "back-propagates into depths and poses only); detach the image tensors or use the reference's PyTorch code")
+
+
 def _shift_of(full, part, what):
     s = 0
     while (part << s) < full:
@@ -83,6 +87,8 @@ class PhotoGeoLoss(torch.autograd.Function):
     def forward(ctx, cfg, tgt_img, intrinsics, *tensors):
         lib = L.load()
         n_ref, n_scales, flags, padding = cfg[:4]
+        if ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:3 + n_ref]):
+            raise NotImplementedError(_NO_IMAGE_GRAD % "photometric / geometry loss")
         sums_allreduce, world = (cfg[5], cfg[6]) if len(cfg) > 5 and cfg[5] is not None else (None, 1)
         tgt_img = L.dev_f32(tgt_img, "tgt_img")
         intrinsics = L.dev_f32(intrinsics, "intrinsics")
@@ -190,6 +196,8 @@ class SmoothLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n, *tensors):
         lib = L.load()
+        if any(ctx.needs_input_grad[2::2]):
+            raise NotImplementedError(_NO_IMAGE_GRAD % "smoothness loss")
         tensors = [L.dev_f32(t, "smooth input") for t in tensors]
         B, _, H, W = tensors[0].shape
         for d, im in zip(tensors[0::2], tensors[1::2]):
@@ -237,6 +245,8 @@ class InverseWarp2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, depth, ref_depth, pose, intrinsics, padding):
         lib = L.load()
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError(_NO_IMAGE_GRAD % "inverse_warp2")
         img, depth, ref_depth, pose, intrinsics = [L.dev_f32(t, "inverse_warp2 input")
                                                    for t in (img, depth, ref_depth, pose, intrinsics)]
         B, _, H, W = img.shape

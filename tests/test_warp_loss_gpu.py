@@ -232,3 +232,26 @@ def test_compute_errors_and_ssim_module(golden_warp):
     x, y = t(g["in_tgt_img"], device=DEV), t(g["in_ref_img0"], device=DEV)
     want = OL.ssim_dissimilarity(t(g["in_tgt_img"]), t(g["in_ref_img0"]))
     np.testing.assert_allclose(lf.compute_ssim_loss(x, y).cpu().numpy(), want.numpy(), atol=1e-5)
+
+
+def test_image_gradients_are_refused_loudly():
+    """The reference propagates gradients into the images too; this implementation does not (the training path never asks for
+    them).  Asking must fail with a clear message instead of silently returning no gradient."""
+    iw, lf = _api()
+    img = torch.rand(2, 3, 16, 16, device=DEV)
+    depth = torch.ones(2, 1, 16, 16, device=DEV, requires_grad=True)
+    pose = torch.zeros(2, 6, device=DEV, requires_grad=True)
+    K = torch.tensor([[20.0, 0, 8], [0, 20.0, 8], [0, 0, 1]], device=DEV).repeat(2, 1, 1)
+    gi = img.clone().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="IMAGES"):
+        iw.inverse_warp2(gi, depth, depth, pose, K)
+    with pytest.raises(NotImplementedError, match="IMAGES"):
+        lf.compute_photo_and_geometry_loss(gi, [img], K, [depth], [[depth]], [pose], [pose], 1, 1, 1, 0, "zeros")
+    with pytest.raises(NotImplementedError, match="IMAGES"):
+        lf.compute_photo_and_geometry_loss(img, [gi], K, [depth], [[depth]], [pose], [pose], 1, 1, 1, 0, "zeros")
+    with pytest.raises(NotImplementedError, match="IMAGES"):
+        lf.compute_smooth_loss([depth], gi, [[depth]], [img])
+    # without image gradients everything works as before
+    p, g = lf.compute_photo_and_geometry_loss(img, [img], K, [depth], [[depth]], [pose], [pose], 1, 1, 1, 0, "zeros")
+    (p + g + lf.compute_smooth_loss([depth], img, [[depth]], [img])).backward()
+    assert depth.grad is not None and pose.grad is not None
