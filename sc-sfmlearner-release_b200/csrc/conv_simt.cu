@@ -463,6 +463,9 @@ bias_grad_kernel(const float* __restrict__ dout, int rows, int C, float* __restr
 }
 
 // host-side launcher shared with the tensor-core weight gradient (conv_tc.cu)
+bool conv_wgrad_thin_eligible(const ScsfmConv& p);                       // conv_wgrad_thin.cu
+int launch_conv_wgrad_thin(const ScsfmConv& p, cudaStream_t st);
+
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st) {
     const int gpr = C / 4;
     if ((C & 3) == 0 && gpr <= 64 && (gpr & (gpr - 1)) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
@@ -526,6 +529,11 @@ extern "C" int scsfm_conv2d_wgrad_simt(const ScsfmConv* p, void* stream) {
     SCSFM_CHECK_ARG(p->dout && p->in && p->dw, "conv2d_wgrad: null tensor");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = p->Cout, N = p->kh * p->kw * p->Cin, Kall = p->B * p->Ho * p->Wo;
+    if (conv_wgrad_thin_eligible(*p) && ((p->tune >> 12) & 3u) != 1u) {       // thin decoder layers: direct kernel (conv_wgrad_thin.cu)
+        if (int rc = launch_conv_wgrad_thin(*p, st)) return rc;
+        if (p->dbias) return launch_bias_grad(p->dout, Kall, M, p->dbias, st);
+        return SCSFM_OK;
+    }
     auto plan = [&](int bm, int bn, dim3& grid, int& kps) {
         const int tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
         int splits = (148 * 4 + tiles - 1) / tiles;

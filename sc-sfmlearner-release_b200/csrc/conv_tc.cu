@@ -836,7 +836,8 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
     int rc;
     ScsfmConv zp = *p;                         // the same layer with zero padding (what the TMA kernel computes)
     zp.pad_mode = SCSFM_PADMODE_ZERO;
-    int kernel = (int)((p->tune >> 12) & 3u);       // SCSFM_TUNE_WGRAD: 0 auto, 1 cp.async kernel, 2 TMA kernel
+    int kernel = (int)((p->tune >> 12) & 3u);       // SCSFM_TUNE_WGRAD: 0 auto, 1 cp.async kernel, 2 TMA kernel, 3 thin-layer fp32 kernel
+    if (kernel == 3 && !conv_wgrad_thin_eligible(*p)) kernel = 0;
     if (kernel == 0) {
         // split-accumulate (parity) mode: the TMA kernel drains its accumulation chains into registers, so it needs no extra
         // split-K to bound the truncation bias; the cp.async kernel does (cheap only when dW is small, i.e. thin layers).
@@ -845,8 +846,13 @@ extern "C" int scsfm_conv2d_wgrad_tc(const ScsfmConv* p, void* stream) {
         // (measured per layer, profiles/r02_layers_tf32x3_wgrad.txt: from 64 output channels up the TMA kernel wins, below
         // that the cp.async kernel with dout / lo(dout) stacked on its N side)
         kernel = (split && p->Cout >= 64) ? 2 : 1;
+        // the 16-output-channel decoder layers are bound by the MMA instruction count (K = 8 pixels per tcgen05.mma, 16 of 128 rows
+        // used) and in split mode read four tensors: the fp32 FMA kernel reads two and is exact per product (conv_wgrad_thin.cu)
+        if (split && conv_wgrad_thin_eligible(*p)) kernel = 3;
     }
-    if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
+    if (kernel == 3) {
+        rc = launch_conv_wgrad_thin(*p, st);
+    } else if (kernel == 2 && p->pad_mode == PADMODE_ZERO && conv_wgrad_tma_eligible(*p)) {
         rc = launch_conv_wgrad_tma(*p, st);
     } else if (kernel == 2 && p->pad_mode == PADMODE_REFLECT && p->pad == 1 && p->Ho >= 3 && p->Wo >= 3 &&
                p->Ho * p->Wo >= 64 * 208 && conv_wgrad_tma_eligible(zp)) {
