@@ -24,6 +24,7 @@ import os
 import subprocess
 import sys
 import threading
+import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "sc-sfmlearner-release_b200")
@@ -198,6 +199,67 @@ def cpu_baseline(config, cfg, steps, warmup, budget_s):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def input_pipeline_extra(cfg, dev, peaks, iters=20):
+    """the training transforms of one batch (flip, zoom-crop, to-tensor, normalise) on the GPU
+    (scsfm.augment.GpuAugment: uint8 frames in, normalised float NCHW out) beside the reference's host chain
+    (custom_transforms.py through PIL / numpy / torch, per sample, one core -- what each of its `-j 4` loader workers runs)."""
+    import random
+    import numpy as np
+    from scsfm.augment import GpuAugment
+    B, H, W, n_img = cfg["batch"], cfg["H"], cfg["W"], cfg["n_ref"] + 1
+    g = np.random.default_rng(5)
+    low = g.integers(0, 256, (n_img, B, H // 8 + 1, W // 8 + 1, 3)).astype(np.float32)
+    frames = np.clip(np.kron(low, np.ones((1, 1, 8, 8, 1), np.float32))[:, :, :H, :W] + g.normal(0, 20, (n_img, B, H, W, 3)), 0, 255).astype(np.uint8)
+    K = np.tile(np.array([[0.58 * W, 0, 0.49 * W], [0, 1.92 * H, 0.47 * H], [0, 0, 1]], np.float32), (B, 1, 1))
+    h_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = h_frames.to(dev)
+    aug = GpuAugment(device=dev)
+    random.seed(0)
+    np.random.seed(0)
+    for _ in range(3):
+        aug(d_frames, K)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        aug(d_frames, K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1) / iters
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        out, _k = aug(h_frames, K)
+        torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / iters
+    alg = 15.0 * n_img * B * H * W           # 3 B/pixel uint8 in + 12 B/pixel float32 out
+    res = {"frames_per_s": round(B / (ms_dev * 1e-3), 1), "ms_per_batch": round(ms_dev, 4), "gbs": round(alg / (ms_dev * 1e-3) / 1e9, 1),
+           "frac_of_hbm_peak": round(alg / (ms_dev * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+           "e2e_frames_per_s": round(B / (ms_e2e * 1e-3), 1), "e2e_ms_per_batch": round(ms_e2e, 4), "h2d_bytes_per_batch": int(frames.size),
+           "how": "%d batches of %d samples x %d frames %dx%d; device: CUDA events around the whole call (host draws + 2 small uploads + 2 kernels), "
+                  "frames resident; e2e: uint8 frames from pinned host memory, synchronised per batch; algorithmic 15 B/pixel" % (iters, B, n_img, H, W)}
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        sys.path.insert(0, ref_dir)
+        import custom_transforms as T       # the reference's (baseline/_ref: unmodified copy made by __graft_entry__.install_reference)
+        chain = T.Compose([T.RandomHorizontalFlip(), T.RandomScaleCrop(), T.ArrayToTensor(), T.Normalize(mean=[0.45] * 3, std=[0.225] * 3)])
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        n = 0
+        while n < 8 or time.perf_counter() - t0 < 2.0:
+            b = n % B
+            chain([frames[i, b].astype(np.float32) for i in range(n_img)], np.copy(K[b]))
+            n += 1
+        per = (time.perf_counter() - t0) / n
+        res["reference_host_chain"] = {"frames_per_s_per_worker": round(1.0 / per, 1), "ms_per_sample": round(per * 1e3, 3), "samples": n,
+                                       "what": "unmodified custom_transforms chain (PIL bicubic + numpy + torch) on one core, decode excluded"}
+    except Exception as e:      # noqa: BLE001
+        res["reference_host_chain"] = {"unavailable": repr(e)}
+    finally:
+        if ref_dir in sys.path:
+            sys.path.remove(ref_dir)
+    return res
+
+
 def run_ours(args):
     import models
     from scsfm import lib as L
@@ -425,6 +487,11 @@ def run_ours(args):
                         "wall clock per iteration incl. its own host syncs and CSV write; inputs resident on the host as in train.py:254-257"
                         % torch.__version__)
         line["gpu_reference"] = gref
+    if world == 1 and not args.no_input_pipeline:
+        try:
+            line["input_pipeline"] = input_pipeline_extra(cfg, dev, peaks)
+        except Exception as e:      # noqa: BLE001  (an extra: never lose the bench line over it)
+            line["input_pipeline"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, cfg, steps=2, warmup=1, budget_s=30.0)
     print(json.dumps(line), flush=True)
@@ -481,6 +548,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-tf32-extra", action="store_true")
+    ap.add_argument("--no-input-pipeline", action="store_true", help="skip the device-side input transforms extra (SURVEY.md 8 f-3)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--overlap-wgrad", type=int, default=1, help="1 (default): weight gradients on a side stream per network (Trainer(overlap_wgrad=True))")
     ap.add_argument("--overlap-nets", type=int, default=1, help="1 (default): PoseResNet on a side stream next to DispResNet (Trainer(overlap_nets=True))")

@@ -293,6 +293,17 @@ int scsfm_spatial_mean_bwd(const float* dout, int B, int HW, int C, float scale,
 int scsfm_compute_errors(const float* gt, const float* pred, int B, int H, int W, int y1, int y2, int x1, int x2,
                          float max_depth, void* work, float* out, void* stream);
 
+/* Training-time image transforms of one batch on the device (reference: custom_transforms.py:21-89 -- RandomHorizontalFlip,
+ * RandomScaleCrop, ArrayToTensor, Normalize -- applied per sample by datasets/sequence_folders.py:59-62; the zoom is Pillow's
+ * 8-bit BICUBIC Image.resize, restated bit for bit).  images [n_img][B][H][W][3] uint8 (decoded frames, image slot major);
+ * params [B][5] int32 ON THE DEVICE = {flip, scaled_w, scaled_h, offset_x, offset_y} per sample (scaled_* >= W / H: the zoomed
+ * size int(W * sx), int(H * sy); offsets inside [0, scaled - size]; {0, W, H, 0, 0} = the validation chain); mean3 / std3: HOST
+ * pointers to three floats; out [n_img][B][3][H][W] float32; workspace: scsfm_augment_workspace_ints(B, H, W) int32, 16-byte
+ * aligned.  No host synchronisation. */
+long long scsfm_augment_workspace_ints(int B, int H, int W);
+int scsfm_augment_batch(const unsigned char* images, const int* params, int n_img, int B, int H, int W, const float* mean3,
+                        const float* std3, float* out, int* workspace, long long workspace_ints, void* stream);
+
 /* out[i] = round-to-nearest TF32 of in[i] (weights of the tensor-core convolutions, once per optimizer step) */
 int scsfm_round_tf32(const float* in, float* out, long long n, void* stream);
 /* lo[i] = tf32(in[i] - trunc_tf32(in[i])): the low part of the split-accumulate operands (ScsfmConv.in_lo / w_lo / dout_lo) */

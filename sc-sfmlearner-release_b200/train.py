@@ -22,6 +22,8 @@ import os
 import shutil
 import time
 
+import numpy as np
+
 import torch
 import torch.distributed as dist
 
@@ -73,16 +75,21 @@ parser.add_argument("--conv-mode", choices=["fp32", "tf32", "tf32x3"], default="
 parser.add_argument("--cuda-graph", type=int, default=1, help="capture the training step in a CUDA graph (single GPU)")
 parser.add_argument("--overlap", type=int, default=1, help="run PoseResNet next to DispResNet and the weight gradients on side streams")
 parser.add_argument("--synthetic-size", type=int, nargs=2, default=[256, 832], metavar=("H", "W"))
+parser.add_argument("--gpu-augment", type=int, default=None, choices=[0, 1],
+                    help="1: the training transforms (flip, zoom-crop, to-tensor, normalise: custom_transforms.py) run on the GPU on uint8 "
+                         "frames (scsfm.augment.GpuAugment, bit-identical to the host chain for equal random draws); 0: the reference's "
+                         "host-side chain inside the loader workers.  Default: 1 for real datasets, 0 for DIR = synthetic")
 
 best_error = -1
 n_iter = 0
 
 
 class SyntheticLoader:
-    """Seeded KITTI/NYU-shaped batches in the dataset's return convention (tgt_img, ref_imgs, K, K_inv)."""
+    """Seeded KITTI/NYU-shaped batches in the dataset's return convention (tgt_img, ref_imgs, K, K_inv); raw=True: the frames
+    as decoded uint8 images [B, n_img, H, W, 3] plus K (what RawFrames below delivers for a real dataset)."""
 
-    def __init__(self, length, batch, H, W, n_ref, kind, seed):
-        self.length, self.args, self.seed = length, (batch, H, W, n_ref, kind), seed
+    def __init__(self, length, batch, H, W, n_ref, kind, seed, raw=False):
+        self.length, self.args, self.seed, self.raw = length, (batch, H, W, n_ref, kind), seed, raw
 
     def __len__(self):
         return self.length
@@ -91,16 +98,59 @@ class SyntheticLoader:
         b, H, W, n_ref, kind = self.args
         for i in range(self.length):
             tgt, refs, K = synth.triplet(self.seed + i, b, H, W, n_ref, kind)
-            yield tgt, refs, K, torch.linalg.inv(K)
+            if self.raw:
+                frames = torch.stack([tgt] + list(refs), 1).permute(0, 1, 3, 4, 2)          # [B, n_img, H, W, 3], normalised
+                yield ((frames * 0.225 + 0.45) * 255).round().clamp(0, 255).to(torch.uint8), K
+            else:
+                yield tgt, refs, K, torch.linalg.inv(K)
 
 
-def make_loaders(args, rank, world):
+class RawFrames(torch.utils.data.Dataset):
+    """A reference dataset built with transform=None (datasets/sequence_folders.py:55-66, pair_folders.py): sample -> (frames
+    uint8 [n_img, H, W, 3] with the target first, intrinsics).  uint8 is exact for decoded JPEG/PNG frames and a quarter of the
+    bytes through the worker pipes and PCIe."""
+
+    def __init__(self, ds):
+        self.ds = ds
+
+    def __len__(self):
+        return len(self.ds)
+
+    def __getitem__(self, i):
+        tgt, refs, K, _ = self.ds[i]
+        return np.stack([tgt] + list(refs)).astype(np.uint8), np.asarray(K, np.float32)
+
+
+class GpuAugmentLoader:
+    """Wraps a loader of (frames uint8 [B, n_img, H, W, 3], K [B, 3, 3]) batches: upload, device-side transforms, and the
+    loop's (tgt_img, ref_imgs, intrinsics, intrinsics_inv) tuple comes out resident on the GPU."""
+
+    def __init__(self, loader, device, train=True):
+        from scsfm.augment import GpuAugment
+        self.loader, self.device = loader, device
+        self.aug = GpuAugment(mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), train=train, device=device)
+        self.sampler = getattr(loader, "sampler", None)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for frames, K in self.loader:
+            frames = frames.to(self.device, non_blocking=True).transpose(0, 1).contiguous()     # image slot major
+            imgs, K = self.aug(frames, K)
+            yield imgs[0], imgs[1:], K, torch.linalg.inv(K)
+
+
+def make_loaders(args, rank, world, device="cuda"):
+    gpu_aug = args.gpu_augment if args.gpu_augment is not None else (0 if args.data == "synthetic" else 1)
     if args.data == "synthetic":
         H, W = args.synthetic_size
         n_ref = 1 if args.folder_type == "pair" else args.sequence_length - 1
         n = args.epoch_size if args.epoch_size > 0 else 100
-        return (SyntheticLoader(n, args.batch_size, H, W, n_ref, args.dataset, 1000 * rank),
-                SyntheticLoader(max(1, n // 10), args.batch_size, H, W, n_ref, args.dataset, 7777 + rank))
+        train_loader = SyntheticLoader(n, args.batch_size, H, W, n_ref, args.dataset, 1000 * rank, raw=bool(gpu_aug))
+        if gpu_aug:
+            train_loader = GpuAugmentLoader(train_loader, device, train=True)
+        return train_loader, SyntheticLoader(max(1, n // 10), args.batch_size, H, W, n_ref, args.dataset, 7777 + rank)
     try:
         import custom_transforms
         from datasets.pair_folders import PairFolder
@@ -112,11 +162,15 @@ def make_loaders(args, rank, world):
     train_tf = custom_transforms.Compose([custom_transforms.RandomHorizontalFlip(), custom_transforms.RandomScaleCrop(),
                                           custom_transforms.ArrayToTensor(), normalize])
     valid_tf = custom_transforms.Compose([custom_transforms.ArrayToTensor(), normalize])
+    if gpu_aug:
+        train_tf = None                      # the datasets hand out the decoded frames; the transforms run on the GPU per batch
     if args.folder_type == "sequence":
         train_set = SequenceFolder(args.data, transform=train_tf, seed=args.seed, train=True,
                                    sequence_length=args.sequence_length, dataset=args.dataset)
     else:
         train_set = PairFolder(args.data, seed=args.seed, train=True, transform=train_tf)
+    if gpu_aug:
+        train_set = RawFrames(train_set)
     if args.with_gt:
         from datasets.validation_folders import ValidationSet
         val_set = ValidationSet(args.data, transform=valid_tf, dataset=args.dataset)
@@ -128,6 +182,8 @@ def make_loaders(args, rank, world):
                                                num_workers=args.workers, pin_memory=True, drop_last=True)
     val_loader = torch.utils.data.DataLoader(val_set, batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
                                              pin_memory=True)
+    if gpu_aug:
+        train_loader = GpuAugmentLoader(train_loader, device, train=True)
     return train_loader, val_loader
 
 
@@ -161,7 +217,7 @@ def main():
         os.makedirs(args.save_path, exist_ok=True)
     torch.manual_seed(args.seed)
 
-    train_loader, val_loader = make_loaders(args, rank, world)
+    train_loader, val_loader = make_loaders(args, rank, world, device)
     if args.epoch_size == 0:
         args.epoch_size = len(train_loader)
 

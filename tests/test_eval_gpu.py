@@ -120,10 +120,11 @@ def test_validate_with_gt_matches_the_oracle():
     np.testing.assert_allclose(got, want / 2, rtol=2e-3, atol=1e-6)
 
 
-def test_train_entry_end_to_end_on_synthetic_data(tmp_path):
+@pytest.mark.parametrize("gpu_augment", [0, 1])
+def test_train_entry_end_to_end_on_synthetic_data(tmp_path, gpu_augment):
     """`python train.py synthetic ...` with the reference's flags: two epochs of three iterations (CUDA-graph step, async logging:
     one read-back per print interval), validation after every epoch, checkpoints and the reference's log files
-    (train.py:219-232,270-290; utils.py:57-66)."""
+    (train.py:219-232,270-290; utils.py:57-66).  gpu_augment = 1: uint8 frames through the device-side transforms."""
     import csv
     import os
     import subprocess
@@ -131,7 +132,8 @@ def test_train_entry_end_to_end_on_synthetic_data(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "sc-sfmlearner-release_b200", "train.py"), "synthetic", "--name", "e2e", "--epochs", "2",
            "--epoch-size", "3", "-b", "2", "--synthetic-size", "128", "160", "--resnet-layers", "18", "--num-scales", "1", "-s", "0.1", "-c", "0.5",
-           "--sequence-length", "3", "--with-ssim", "1", "--with-mask", "1", "--with-auto-mask", "1", "--with-pretrain", "0", "--print-freq", "2"]
+           "--sequence-length", "3", "--with-ssim", "1", "--with-mask", "1", "--with-auto-mask", "1", "--with-pretrain", "0", "--print-freq", "2",
+           "--gpu-augment", str(gpu_augment)]
     out = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     assert " * epoch 1 train loss" in out.stdout
