@@ -141,6 +141,31 @@ class GpuAugmentLoader:
             yield imgs[0], imgs[1:], K, torch.linalg.inv(K)
 
 
+def _reference_dataset_module(name):
+    """datasets/<name>.py of the reference, loaded by file path from the first sys.path entry that holds it.  The reference's
+    datasets/ directory has no __init__.py (a namespace package), so a plain `import datasets.<name>` resolves to any installed
+    regular package called `datasets` (HuggingFace's) instead -- regular packages win over namespace packages whatever the
+    path order.  The module is registered under a private name (picklable for loader workers); sys.modules['datasets'] is left alone."""
+    import importlib.util
+    import sys
+    key = "scsfm_reference_datasets_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    for entry in sys.path:
+        f = os.path.join(entry or ".", "datasets", name + ".py")
+        if os.path.isfile(f):
+            spec = importlib.util.spec_from_file_location(key, f)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[key] = mod
+            try:
+                spec.loader.exec_module(mod)
+            except BaseException:
+                del sys.modules[key]
+                raise
+            return mod
+    raise ImportError("datasets/%s.py not found on sys.path" % name)
+
+
 def make_loaders(args, rank, world, device="cuda"):
     gpu_aug = args.gpu_augment if args.gpu_augment is not None else (0 if args.data == "synthetic" else 1)
     if args.data == "synthetic":
@@ -153,8 +178,8 @@ def make_loaders(args, rank, world, device="cuda"):
         return train_loader, SyntheticLoader(max(1, n // 10), args.batch_size, H, W, n_ref, args.dataset, 7777 + rank)
     try:
         import custom_transforms
-        from datasets.pair_folders import PairFolder
-        from datasets.sequence_folders import SequenceFolder
+        PairFolder = _reference_dataset_module("pair_folders").PairFolder
+        SequenceFolder = _reference_dataset_module("sequence_folders").SequenceFolder
     except ImportError as e:
         raise SystemExit("real datasets need the reference's host-side loaders (datasets/*.py, custom_transforms.py) on "
                          "PYTHONPATH -- they are out of scope of this repo (%s); or pass DIR = synthetic" % e)
@@ -172,7 +197,7 @@ def make_loaders(args, rank, world, device="cuda"):
     if gpu_aug:
         train_set = RawFrames(train_set)
     if args.with_gt:
-        from datasets.validation_folders import ValidationSet
+        ValidationSet = _reference_dataset_module("validation_folders").ValidationSet
         val_set = ValidationSet(args.data, transform=valid_tf, dataset=args.dataset)
     else:
         val_set = SequenceFolder(args.data, transform=valid_tf, seed=args.seed, train=False,

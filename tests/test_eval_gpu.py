@@ -150,3 +150,32 @@ def test_train_entry_end_to_end_on_synthetic_data(tmp_path, gpu_augment):
     assert summary[0] == ["train_loss", "validation_loss"] and len(summary) == 3
     ck = torch.load(d / "dispnet_checkpoint.pth.tar")
     assert ck["epoch"] == 2 and "encoder.encoder.conv1.weight" in ck["state_dict"]
+
+
+@pytest.mark.parametrize("gpu_augment", [0, 1])
+def test_train_entry_on_a_dataset_on_disk(tmp_path, gpu_augment):
+    """`python train.py DIR ...` on a tiny JPEG dataset in the reference's folder layout, with the reference's own dataset
+    classes (unmodified copy under baseline/_ref) on PYTHONPATH as train.py expects: --gpu-augment 0 = the reference's host
+    transform chain in the loader, 1 = uint8 frames + the device-side transforms; training epoch, validation, checkpoints."""
+    import os
+    import subprocess
+    import sys
+    from helpers import make_disk_dataset, reference_loader_env
+    env = reference_loader_env()
+    if env is None:
+        pytest.skip("baseline/_ref (copy of the reference made by __graft_entry__.build()) is not present")
+    data = make_disk_dataset(str(tmp_path / "data"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "sc-sfmlearner-release_b200", "train.py"), data, "--name", "disk", "--epochs", "1",
+           "--epoch-size", "2", "-b", "2", "-j", "0", "--resnet-layers", "18", "--num-scales", "1", "-s", "0.1", "-c", "0.5",
+           "--sequence-length", "3", "--with-ssim", "1", "--with-mask", "1", "--with-auto-mask", "1", "--with-pretrain", "0",
+           "--print-freq", "1", "--gpu-augment", str(gpu_augment)]
+    out = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert " * epoch 0 train loss" in out.stdout or "train loss" in out.stdout, out.stdout[-2000:]
+    runs = os.listdir(tmp_path / "checkpoints" / "disk")
+    d = tmp_path / "checkpoints" / "disk" / runs[0]
+    assert {"dispnet_checkpoint.pth.tar", "exp_pose_checkpoint.pth.tar", "progress_log_full.csv"} <= set(os.listdir(d))
+    import csv
+    full = list(csv.reader(open(d / "progress_log_full.csv"), delimiter="\t"))
+    assert len(full) == 1 + 2 and all(np.isfinite(float(v)) for row in full[1:] for v in row)

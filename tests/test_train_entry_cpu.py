@@ -70,3 +70,39 @@ def test_cli_defaults_and_pretrained_weights(tmp_path, monkeypatch):
     d, p = models.DispResNet(18, True), models.PoseResNet(18, True)
     assert torch.equal(d.encoder.encoder.layer2[0].conv1.weight, src["layer2.0.conv1.weight"])
     assert torch.allclose(p.encoder.encoder.conv1.weight, torch.cat([src["conv1.weight"]] * 2, 1) / 2)
+
+
+def test_real_dataset_loaders_host_side(tmp_path):
+    """train.make_loaders on a dataset on disk with the reference's own dataset classes on PYTHONPATH: --gpu-augment 0 builds the
+    reference's host chain (normalised float tensors come out of the loader), --gpu-augment 1 builds the datasets with
+    transform=None and hands uint8 frames [B, n_img, H, W, 3] + intrinsics to the device stage (host side checked here, in a clean
+    interpreter; the device stage in tests/test_augment_gpu.py and tests/test_eval_gpu.py)."""
+    from helpers import make_disk_dataset, reference_loader_env
+    env = reference_loader_env()
+    if env is None:
+        pytest.skip("baseline/_ref (copy of the reference made by __graft_entry__.build()) is not present")
+    data = make_disk_dataset(str(tmp_path / "data"))
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sc-sfmlearner-release_b200")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np, torch, train as T\n"
+            "SF = T._reference_dataset_module('sequence_folders'); assert 'baseline' in SF.__file__, SF.__file__\n"
+            "for g in (0, 1):\n"
+            "    args = T.parser.parse_args([%r, '--name', 'x', '-b', '2', '-j', '0', '--gpu-augment', str(g)])\n"
+            "    class NoGpu(T.GpuAugmentLoader):\n"
+            "        def __init__(self, loader, device, train=True): self.loader = loader\n"
+            "    T.GpuAugmentLoader = NoGpu\n"
+            "    tl, vl = T.make_loaders(args, 0, 1, 'cpu')\n"
+            "    if g == 0:\n"
+            "        tgt, refs, K, Kinv = next(iter(tl))\n"
+            "        print('HOST', tuple(tgt.shape), tgt.dtype, len(refs), tuple(K.shape), float(tgt.mean()) < 3, len(tl))\n"
+            "    else:\n"
+            "        frames, K = next(iter(tl.loader))\n"
+            "        print('RAW', tuple(frames.shape), frames.dtype, tuple(K.shape), K.dtype, len(tl.loader))\n"
+            "    tgt, refs, K, Kinv = next(iter(vl))\n"
+            "    print('VAL', tuple(tgt.shape), len(refs), len(vl))\n" % (pkg, data))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "HOST (2, 3, 128, 160) torch.float32 2 (2, 3, 3) True 3", lines
+    assert lines[2] == "RAW (2, 3, 128, 160, 3) torch.uint8 (2, 3, 3) torch.float32 3", lines
+    assert lines[1] == lines[3] == "VAL (2, 3, 128, 160) 2 2", lines
