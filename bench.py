@@ -242,14 +242,18 @@ def input_pipeline_extra(cfg, dev, peaks, iters=20):
         sys.path.insert(0, ref_dir)
         import custom_transforms as T       # the reference's (baseline/_ref: unmodified copy made by __graft_entry__.install_reference)
         chain = T.Compose([T.RandomHorizontalFlip(), T.RandomScaleCrop(), T.ArrayToTensor(), T.Normalize(mean=[0.45] * 3, std=[0.225] * 3)])
+        nthreads = torch.get_num_threads()
         torch.set_num_threads(1)
-        t0 = time.perf_counter()
-        n = 0
-        while n < 8 or time.perf_counter() - t0 < 2.0:
-            b = n % B
-            chain([frames[i, b].astype(np.float32) for i in range(n_img)], np.copy(K[b]))
-            n += 1
-        per = (time.perf_counter() - t0) / n
+        try:
+            t0 = time.perf_counter()
+            n = 0
+            while n < 8 or time.perf_counter() - t0 < 2.0:
+                b = n % B
+                chain([frames[i, b].astype(np.float32) for i in range(n_img)], np.copy(K[b]))
+                n += 1
+            per = (time.perf_counter() - t0) / n
+        finally:
+            torch.set_num_threads(nthreads)
         res["reference_host_chain"] = {"frames_per_s_per_worker": round(1.0 / per, 1), "ms_per_sample": round(per * 1e3, 3), "samples": n,
                                        "what": "unmodified custom_transforms chain (PIL bicubic + numpy + torch) on one core, decode excluded"}
     except Exception as e:      # noqa: BLE001

@@ -462,10 +462,10 @@ bias_grad_kernel(const float* __restrict__ dout, int rows, int C, float* __restr
     }
 }
 
-// host-side launcher shared with the tensor-core weight gradient (conv_tc.cu)
 bool conv_wgrad_thin_eligible(const ScsfmConv& p);                       // conv_wgrad_thin.cu
 int launch_conv_wgrad_thin(const ScsfmConv& p, cudaStream_t st);
 
+// host-side launcher shared with the tensor-core weight gradient (conv_tc.cu)
 int launch_bias_grad(const float* dout, int rows, int C, float* dbias, cudaStream_t st) {
     const int gpr = C / 4;
     if ((C & 3) == 0 && gpr <= 64 && (gpr & (gpr - 1)) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
