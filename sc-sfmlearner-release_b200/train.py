@@ -200,8 +200,10 @@ def make_loaders(args, rank, world, device="cuda"):
         ValidationSet = _reference_dataset_module("validation_folders").ValidationSet
         val_set = ValidationSet(args.data, transform=valid_tf, dataset=args.dataset)
     else:
-        val_set = SequenceFolder(args.data, transform=valid_tf, seed=args.seed, train=False,
+        val_set = SequenceFolder(args.data, transform=None if gpu_aug else valid_tf, seed=args.seed, train=False,
                                  sequence_length=args.sequence_length, dataset=args.dataset)
+        if gpu_aug:
+            val_set = RawFrames(val_set)     # (the ground-truth validation set above keeps the host chain: it also returns depth maps)
     sampler = torch.utils.data.distributed.DistributedSampler(train_set, world, rank, shuffle=True, seed=args.seed) if world > 1 else None
     train_loader = torch.utils.data.DataLoader(train_set, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
                                                num_workers=args.workers, pin_memory=True, drop_last=True)
@@ -209,6 +211,8 @@ def make_loaders(args, rank, world, device="cuda"):
                                              pin_memory=True)
     if gpu_aug:
         train_loader = GpuAugmentLoader(train_loader, device, train=True)
+        if not args.with_gt:
+            val_loader = GpuAugmentLoader(val_loader, device, train=False)      # ArrayToTensor + Normalize only
     return train_loader, val_loader
 
 

@@ -98,11 +98,15 @@ def test_real_dataset_loaders_host_side(tmp_path):
             "    else:\n"
             "        frames, K = next(iter(tl.loader))\n"
             "        print('RAW', tuple(frames.shape), frames.dtype, tuple(K.shape), K.dtype, len(tl.loader))\n"
-            "    tgt, refs, K, Kinv = next(iter(vl))\n"
-            "    print('VAL', tuple(tgt.shape), len(refs), len(vl))\n" % (pkg, data))
+            "    if g == 0:\n"
+            "        tgt, refs, K, Kinv = next(iter(vl))\n"
+            "        print('VAL', tuple(tgt.shape), len(refs), len(vl))\n"
+            "    else:\n"
+            "        frames, K = next(iter(vl.loader))\n"
+            "        print('VALRAW', tuple(frames.shape), frames.dtype, len(vl.loader))\n" % (pkg, data))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = out.stdout.strip().splitlines()
     assert lines[0] == "HOST (2, 3, 128, 160) torch.float32 2 (2, 3, 3) True 3", lines
     assert lines[2] == "RAW (2, 3, 128, 160, 3) torch.uint8 (2, 3, 3) torch.float32 3", lines
-    assert lines[1] == lines[3] == "VAL (2, 3, 128, 160) 2 2", lines
+    assert lines[1] == "VAL (2, 3, 128, 160) 2 2" and lines[3] == "VALRAW (2, 3, 128, 160, 3) torch.uint8 2", lines
